@@ -1,0 +1,101 @@
+// C-ABI plumbing: version, thread-local error text, device check, launch counter, test hooks.
+#include <stdarg.h>
+#include <string.h>
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "misc.cuh"
+
+namespace dvd {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+void count_launch(int n) { g_launches += n; }
+
+}  // namespace dvd
+
+using namespace dvd;
+
+extern "C" int dvd_version(void) { return DVD_ABI_VERSION; }
+extern "C" const char* dvd_last_error(void) { return g_err; }
+extern "C" long long dvd_launch_count(int reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+extern "C" int dvd_check_device(void) {
+  int dev = 0;
+  DVD_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  DVD_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (p.major != 10) {
+    set_error("device %d is sm_%d%d; libdvd_b200 is built for sm_100a only", dev, p.major, p.minor);
+    return DVD_E_ARCH;
+  }
+  return 0;
+}
+
+// A[M,K] fp32, W[N,K] fp32 -> C[M,N] = A W^T + bias.  In bf16 mode the operands are first rounded
+// to bf16 into `scratch` (needs (M+N)*K*2 bytes) and the tcgen05 kernel is used.
+extern "C" int dvd_test_gemm(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int precision,
+                             void* scratch, size_t scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DVD_REQUIRE(A && W && C, "test_gemm: null");
+  Epilogue e; e.bias = bias; e.out = C; e.ldc = N;
+  if (precision == DVD_PREC_FP32) {
+    GemmParams p = linear_params(A, K, W, M, N, K);
+    p.e = e;
+    return gemm_f32(p, A_DIRECT, B_NK, 1, st);
+  }
+  size_t need = ((size_t)M + N) * K * 2 + 512;
+  DVD_REQUIRE(scratch && scratch_bytes >= need, "test_gemm: scratch needs %zu bytes", need);
+  __nv_bfloat16* A16 = (__nv_bfloat16*)scratch;
+  __nv_bfloat16* W16 = (__nv_bfloat16*)((char*)scratch + (((size_t)M * K * 2 + 255) & ~size_t(255)));
+  int rc = f32_to_bf16(A, A16, (long long)M * K, st); if (rc) return rc;
+  rc = f32_to_bf16(W, W16, (long long)N * K, st); if (rc) return rc;
+  return gemm_tc_bf16(A16, K, W16, K, M, N, K, e, st);
+}
+
+// q,k,v,o: [batch, T, heads*d] fp32.  fp32 mode: scratch holds the [batch*heads, T, T] scores.
+extern "C" int dvd_test_attention(const float* q, const float* k, const float* v, float* o, int batch, int heads, int T, int d,
+                                  float scale, int precision, void* scratch, size_t scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DVD_REQUIRE(q && k && v && o && scratch, "test_attention: null");
+  const int ld = heads * d;
+  if (precision == DVD_PREC_FP32) {
+    size_t per = (size_t)heads * T * T;
+    DVD_REQUIRE(scratch_bytes >= per * batch * 4, "test_attention: scratch needs %zu bytes", per * batch * 4);
+    float* S = (float*)scratch;
+    GemmParams p;
+    p.A = q; p.lda = ld; p.sAn = (long long)T * ld; p.sAh = d;
+    p.B = k; p.ldb = ld; p.sBn = (long long)T * ld; p.sBh = d;
+    p.M = T; p.N = T; p.K = d; p.heads = heads; p.alpha = scale;
+    p.e.out = S; p.e.ldc = T; p.sCn = (long long)per; p.sCh = (long long)T * T;
+    int rc = gemm_f32(p, A_DIRECT, B_NK, batch * heads, st); if (rc) return rc;
+    rc = softmax_rows(S, (long long)batch * heads * T, T, st); if (rc) return rc;
+    GemmParams g;
+    g.A = S; g.lda = T; g.sAn = (long long)per; g.sAh = (long long)T * T;
+    g.B = v; g.ldb = ld; g.sBn = (long long)T * ld; g.sBh = d;
+    g.M = T; g.N = d; g.K = T; g.heads = heads;
+    g.e.out = o; g.e.ldc = ld; g.sCn = (long long)T * ld; g.sCh = d;
+    return gemm_f32(g, A_DIRECT, B_KN, batch * heads, st);
+  }
+  size_t n = (size_t)batch * T * ld;
+  DVD_REQUIRE(scratch_bytes >= n * 2 * 4 + 4 * n, "test_attention: scratch needs %zu bytes", n * 12);
+  __nv_bfloat16* q16 = (__nv_bfloat16*)scratch; __nv_bfloat16* k16 = q16 + n; __nv_bfloat16* v16 = k16 + n; __nv_bfloat16* o16 = v16 + n;
+  int rc = f32_to_bf16(q, q16, n, st); if (rc) return rc;
+  rc = f32_to_bf16(k, k16, n, st); if (rc) return rc;
+  rc = f32_to_bf16(v, v16, n, st); if (rc) return rc;
+  rc = attention_tc_bf16(q16, ld, k16, ld, v16, ld, o16, ld, batch, heads, T, d, scale, 1, st); if (rc) return rc;
+  return bf16_to_f32(o16, o, n, st);
+}

@@ -1,0 +1,76 @@
+// fp32 FFMA GEMM (DVD_PREC_FP32 mode) with fused epilogues; also the implicit-GEMM 3x3 conv of the
+// pyramid and the batched QK^T / PV products of the fp32 attention path.
+//
+//   C[M,N] = epilogue( alpha * A[M,K] * B )      B given K-major (W[n][k], torch Linear layout)
+//                                                 or N-major (B[k][n], used for P*V)
+// 128 x BN x 16 tiles, 256 threads, 8 x (BN/16) register micro-tile, double-buffered smem with
+// register-staged global prefetch.  This is the bit-reproducible reference mode of the library;
+// the tensor-core (tcgen05) path in gemm_tc.cu shares the Epilogue description below.
+#pragma once
+#include "common.cuh"
+
+namespace dvd {
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 };
+
+struct Epilogue {
+  const float* bias = nullptr;        // [N]
+  const float* scale = nullptr;       // [N]  folded BN: v = v*scale + shift
+  const float* shift = nullptr;
+  int act = ACT_NONE;
+  const float* pos = nullptr;         // [pos_rows, N] added by (row % pos_rows)
+  int pos_rows = 0;
+  const float* gate = nullptr;        // [N]  v *= gate
+  const float* resid = nullptr;       // [resid_rows or M, ldr] residual added last
+  int ldr = 0;
+  int resid_mod = 0;                  // 0: resid row = row ; else row % resid_mod
+  float* out = nullptr;
+  int ldc = 0;
+  int group_rows = 0;                 // 0: identity ; else out row = row % group_rows,
+  int group_col_stride = 0;           //               out col += (row / group_rows) * group_col_stride
+  __nv_bfloat16* out_bf16 = nullptr;  // optional bf16 copy of the output (same mapping, ld = ldc_bf16)
+  int ldc_bf16 = 0;
+};
+
+__device__ __forceinline__ float apply_epilogue(const Epilogue& e, float v, int row, int col, int N) {
+  if (e.bias) v += __ldg(e.bias + col);
+  if (e.scale) v = v * __ldg(e.scale + col) + __ldg(e.shift + col);
+  if (e.act == ACT_RELU) v = fmaxf(v, 0.f);
+  else if (e.act == ACT_GELU) v = gelu_tanh(v);
+  else if (e.act == ACT_SIGMOID) v = sigmoidf_(v);
+  if (e.pos) v += __ldg(e.pos + (size_t)(row % e.pos_rows) * N + col);
+  if (e.gate) v *= __ldg(e.gate + col);
+  if (e.resid) {
+    int rr = e.resid_mod ? (row % e.resid_mod) : row;
+    v += __ldg(e.resid + (size_t)rr * e.ldr + col);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void epilogue_dest(const Epilogue& e, int row, int col, int& orow, int& ocol) {
+  if (e.group_rows) { orow = row % e.group_rows; ocol = col + (row / e.group_rows) * e.group_col_stride; }
+  else { orow = row; ocol = col; }
+}
+
+enum { A_DIRECT = 0, A_CONV3 = 1 };
+enum { B_NK = 0, B_KN = 1 };
+
+struct GemmParams {
+  const float* A = nullptr; long long lda = 0;
+  int convH = 0, convW = 0, convC = 0;          // A_CONV3: NHWC input, K = 9*convC
+  const float* B = nullptr; long long ldb = 0;
+  int M = 0, N = 0, K = 0;
+  int heads = 1, bdiv = 1;                      // blockIdx.z = n*heads + h ; B batch index = n / bdiv
+  long long sAn = 0, sAh = 0, sBn = 0, sBh = 0, sCn = 0, sCh = 0;
+  float alpha = 1.f;
+  Epilogue e;
+};
+
+int gemm_f32(const GemmParams& p, int amode, int bmode, int batch, cudaStream_t st);
+
+// convenience: C = epi(A * W^T), W K-major
+inline GemmParams linear_params(const float* A, int lda, const float* W, int M, int N, int K) {
+  GemmParams p; p.A = A; p.lda = lda; p.B = W; p.ldb = K; p.M = M; p.N = N; p.K = K; return p;
+}
+
+}  // namespace dvd

@@ -1,0 +1,18 @@
+// tcgen05 / TMEM / TMA tensor-core path (DVD_PREC_BF16): dense GEMM with the shared Epilogue and
+// flash attention.  Implemented in gemm_tc.cu / attn_tc.cu.
+#pragma once
+#include "gemm_simt.cuh"
+
+namespace dvd {
+
+// C[M,N] = epilogue(A[M,K] * W[N,K]^T), A/W bf16 row-major (K contiguous), fp32 accumulate in TMEM.
+int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e,
+                 cudaStream_t st);
+
+// softmax(scale * Q K^T) V per (sample, head); bf16 in/out, fp32 softmax statistics and accumulation.
+// q/k/v/o row-major with leading dims ld*, head h at columns [h*d, (h+1)*d); k/v of sample n come
+// from sample n / kv_div.  d in {64, 256}, T multiple of 128.
+int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
+                      __nv_bfloat16* o, int ldo, int nsamp, int heads, int T, int d, float scale, int kv_div, cudaStream_t st);
+
+}  // namespace dvd

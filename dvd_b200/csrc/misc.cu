@@ -1,0 +1,555 @@
+#include "misc.cuh"
+
+namespace dvd {
+
+// ------------------------------------------------------------------------------------------ layer norm
+template <int NV>   // float4 per lane: C = 128 * NV
+__global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ in, int ldin, float* __restrict__ out, int ldo,
+                                                   __nv_bfloat16* __restrict__ out16, int ldo16, int rows, float eps,
+                                                   const float* __restrict__ w, const float* __restrict__ b,
+                                                   const float* __restrict__ msh, const float* __restrict__ msc) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  constexpr int C = 128 * NV;
+  const float4* x4 = reinterpret_cast<const float4*>(in + (size_t)row * ldin);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { v[i] = __ldg(x4 + lane + 32 * i); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (lane + 32 * i) * 4;
+    float y[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+    if (w) {
+      float4 ww = __ldg(reinterpret_cast<const float4*>(w + c0)), bb = __ldg(reinterpret_cast<const float4*>(b + c0));
+      y[0] = y[0] * ww.x + bb.x; y[1] = y[1] * ww.y + bb.y; y[2] = y[2] * ww.z + bb.z; y[3] = y[3] * ww.w + bb.w;
+    }
+    if (msc) {
+      float4 sc = __ldg(reinterpret_cast<const float4*>(msc + c0)), sh = __ldg(reinterpret_cast<const float4*>(msh + c0));
+      y[0] = y[0] * (1.f + sc.x) + sh.x; y[1] = y[1] * (1.f + sc.y) + sh.y;
+      y[2] = y[2] * (1.f + sc.z) + sh.z; y[3] = y[3] * (1.f + sc.w) + sh.w;
+    }
+    if (out) *reinterpret_cast<float4*>(out + (size_t)row * ldo + c0) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out16) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+      uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(out16 + (size_t)row * ldo16 + c0) = u;
+    }
+  }
+}
+
+int layernorm(const float* in, int ldin, float* out, int ldo, __nv_bfloat16* out16, int ldo16, int rows, int C, float eps,
+              const float* w, const float* b, const float* msh, const float* msc, cudaStream_t st) {
+  DVD_REQUIRE(in && (out || out16) && rows > 0, "layernorm: bad args");
+  DVD_REQUIRE(C == 384 || C == 1536, "layernorm: C must be 384 or 1536 (got %d)", C);
+  DVD_REQUIRE(ldin % 4 == 0 && ldo % 4 == 0 && ldo16 % 4 == 0, "layernorm: ld %% 4");
+  dim3 grid(cdiv(rows, 8));
+  if (C == 384) k_layernorm<3><<<grid, 256, 0, st>>>(in, ldin, out, ldo, out16, ldo16, rows, eps, w, b, msh, msc);
+  else          k_layernorm<12><<<grid, 256, 0, st>>>(in, ldin, out, ldo, out16, ldo16, rows, eps, w, b, msh, msc);
+  DVD_LAUNCH_CHECK("k_layernorm");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ layout kernels
+__global__ void k_pack_y4(const float* __restrict__ y, const float* __restrict__ m, float* __restrict__ out, int B) {
+  const size_t plane = 512 * 512;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane * B) return;
+  size_t b = i / plane, px = i % plane;
+  const float* yb = y + b * 3 * plane;
+  float4 v = make_float4(__ldg(yb + px), __ldg(yb + plane + px), __ldg(yb + 2 * plane + px), __ldg(m + b * plane + px));
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+int pack_y4(const float* y512, const float* mask, float* out, int B, cudaStream_t st) {
+  DVD_REQUIRE(y512 && mask && out && B > 0, "pack_y4: bad args");
+  k_pack_y4<<<cdiv((long long)B * 512 * 512, 256), 256, 0, st>>>(y512, mask, out, B);
+  DVD_LAUNCH_CHECK("k_pack_y4");
+  return 0;
+}
+
+__global__ void k_maxpool2(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W, int C4) {
+  const int Ho = H / 2, Wo = W / 2;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * Ho * Wo * C4;
+  if (i >= total) return;
+  int c = i % C4; size_t r = i / C4;
+  int xo = r % Wo; r /= Wo;
+  int yo = r % Ho; int b = r / Ho;
+  const float4* p = in + (((size_t)b * H + 2 * yo) * W + 2 * xo) * C4 + c;
+  float4 a = __ldg(p), bb = __ldg(p + C4), cc = __ldg(p + (size_t)W * C4), d = __ldg(p + (size_t)W * C4 + C4);
+  out[i] = make_float4(fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, d.x)), fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, d.y)),
+                       fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, d.z)), fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, d.w)));
+}
+int maxpool2_nhwc(const float* in, float* out, int B, int H, int W, int C, cudaStream_t st) {
+  DVD_REQUIRE(in && out && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2: bad args");
+  size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 4);
+  k_maxpool2<<<cdiv(total, 256), 256, 0, st>>>((const float4*)in, (float4*)out, B, H, W, C / 4);
+  DVD_LAUNCH_CHECK("k_maxpool2");
+  return 0;
+}
+
+__global__ void k_nhwc_to_nchw(const float* __restrict__ in, float* __restrict__ out, int HW, int C) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int p = p0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < HW && c < C) ? in[((size_t)b * HW + p) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int c = c0 + r, p = p0 + threadIdx.x;
+    if (p < HW && c < C) out[((size_t)b * C + c) * HW + p] = tile[threadIdx.x][r];
+  }
+}
+int nhwc_to_nchw(const float* in, float* out, int B, int H, int W, int C, cudaStream_t st) {
+  DVD_REQUIRE(in && out, "nhwc_to_nchw: null");
+  k_nhwc_to_nchw<<<dim3(cdiv(H * W, 32), cdiv(C, 32), B), dim3(32, 8), 0, st>>>(in, out, H * W, C);
+  DVD_LAUNCH_CHECK("k_nhwc_to_nchw");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ patchify
+__device__ __forceinline__ void store4(float* A, __nv_bfloat16* A16, size_t off, float a, float b, float c, float d) {
+  if (A) *reinterpret_cast<float4*>(A + off) = make_float4(a, b, c, d);
+  if (A16) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(A16 + off) = u;
+  }
+}
+
+// block = one (b, h) token row x 32 channels; smem tile gives coalesced reads AND writes
+__global__ void __launch_bounds__(256) k_patchify_nchw(const float* __restrict__ in, float* __restrict__ A,
+                                                       __nv_bfloat16* __restrict__ A16, int lda, int C) {
+  __shared__ float tile[32][2][65];
+  const int h = blockIdx.x, c0 = blockIdx.y * 32, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+    int cc = i / 128, r = (i % 128) / 64, x = i % 64;
+    int c = c0 + cc;
+    tile[cc][r][x] = (c < C) ? __ldg(in + (((size_t)b * C + c) * 64 + 2 * h + r) * 64 + x) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {       // (w, cc)
+    int w = i / 32, cc = i % 32, c = c0 + cc;
+    if (c >= C) continue;
+    size_t off = ((size_t)(b * 32 + h) * 32 + w) * lda + (size_t)c * 4;
+    store4(A, A16, off, tile[cc][0][2 * w], tile[cc][0][2 * w + 1], tile[cc][1][2 * w], tile[cc][1][2 * w + 1]);
+  }
+}
+int patchify_nchw(const float* in, float* A, __nv_bfloat16* A16, int lda, int B, int C, cudaStream_t st) {
+  DVD_REQUIRE(in && (A || A16) && lda % 4 == 0 && lda >= 4 * C, "patchify_nchw: bad args");
+  k_patchify_nchw<<<dim3(32, cdiv(C, 32), B), 256, 0, st>>>(in, A, A16, lda, C);
+  DVD_LAUNCH_CHECK("k_patchify_nchw");
+  return 0;
+}
+
+__global__ void k_patchify_nhwc(const float* __restrict__ in, float* __restrict__ A, __nv_bfloat16* __restrict__ A16, int lda,
+                                int C, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = i % C; size_t row = i / C;          // row = (b*32 + h)*32 + w
+  int w = row % 32, h = (row / 32) % 32; size_t b = row / 1024;
+  const float* p = in + ((b * 64 + 2 * h) * 64 + 2 * w) * C + c;
+  store4(A, A16, row * lda + (size_t)c * 4, __ldg(p), __ldg(p + C), __ldg(p + 64 * C), __ldg(p + 65 * C));
+}
+int patchify_nhwc(const float* in, float* A, __nv_bfloat16* A16, int lda, int B, int C, cudaStream_t st) {
+  DVD_REQUIRE(in && (A || A16) && lda % 4 == 0 && lda >= 4 * C, "patchify_nhwc: bad args");
+  size_t total = (size_t)B * 1024 * C;
+  k_patchify_nhwc<<<cdiv(total, 256), 256, 0, st>>>(in, A, A16, lda, C, total);
+  DVD_LAUNCH_CHECK("k_patchify_nhwc");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ r operand (+ feature warp)
+__global__ void __launch_bounds__(256) k_build_r(const float* __restrict__ flow, const float* __restrict__ feat,
+                                                 const float* __restrict__ init_feat, int init_feat_div, int mode,
+                                                 float* __restrict__ A, __nv_bfloat16* __restrict__ A16, int lda, int n_hyp) {
+  const int row = blockIdx.x;                  // (n*32 + h)*32 + w
+  const int w = row % 32, h = (row / 32) % 32, n = row / 1024;
+  const int c = threadIdx.x;                   // feature channel 0..255
+  const float* fl = flow + (size_t)n * 2 * 4096;
+  const float* ft = feat + (size_t)(n / n_hyp) * 4096 * 256;
+  float v[4];
+#pragma unroll
+  for (int pq = 0; pq < 4; ++pq) {
+    const int y = 2 * h + (pq >> 1), x = 2 * w + (pq & 1);
+    if (mode == FEAT_EXPLICIT_OR_ZERO) {
+      v[pq] = init_feat ? __ldg(init_feat + (((size_t)(n / init_feat_div) * 256 + c) * 64 + y) * 64 + x) : 0.f;
+    } else if (mode == FEAT_ASIS) {
+      v[pq] = __ldg(ft + ((size_t)y * 64 + x) * 256 + c);
+    } else {
+      // GD:618-624: grid = (pred_flow + base64)*2 - 1 ; base64 = coords/63 ; WP:73 grid_sample
+      float gx = (__ldg(fl + y * 64 + x) + (float)x / 63.0f) * 2.0f - 1.0f;
+      float gy = (__ldg(fl + 4096 + y * 64 + x) + (float)y / 63.0f) * 2.0f - 1.0f;
+      float ix = ((gx + 1.f) / 2.f) * 63.f, iy = ((gy + 1.f) / 2.f) * 63.f;
+      float fx = fminf(fmaxf(floorf(ix), -2.f), 65.f), fy = fminf(fmaxf(floorf(iy), -2.f), 65.f);
+      int x0 = (int)fx, y0 = (int)fy;
+      float ax = ix - fx, ay = iy - fy, bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy;
+      bool vx0 = x0 >= 0 && x0 < 64, vx1 = x0 + 1 >= 0 && x0 + 1 < 64, vy0 = y0 >= 0 && y0 < 64, vy1 = y0 + 1 >= 0 && y0 + 1 < 64;
+      const float* p = ft + ((long long)y0 * 64 + x0) * 256 + c;
+      float acc = 0.f;
+      if (vy0 && vx0) acc += __ldg(p) * (bx * by);
+      if (vy0 && vx1) acc += __ldg(p + 256) * (ax * by);
+      if (vy1 && vx0) acc += __ldg(p + 64 * 256) * (bx * ay);
+      if (vy1 && vx1) acc += __ldg(p + 65 * 256) * (ax * ay);
+      v[pq] = acc;
+    }
+  }
+  store4(A, A16, (size_t)row * lda + 8 + (size_t)c * 4, v[0], v[1], v[2], v[3]);
+  if (c < 2) {   // flow channels: k = c*4 + p*2 + q
+    const float* p = fl + (size_t)c * 4096 + (2 * h) * 64 + 2 * w;
+    store4(A, A16, (size_t)row * lda + (size_t)c * 4, __ldg(p), __ldg(p + 1), __ldg(p + 64), __ldg(p + 65));
+  }
+  // zero the K padding (lda may exceed 1032 for the tensor-core path)
+  for (int k = 1032 + c; k < lda; k += 256) {
+    if (A) A[(size_t)row * lda + k] = 0.f;
+    if (A16) A16[(size_t)row * lda + k] = __float2bfloat16_rn(0.f);
+  }
+}
+int build_r_operand(const float* init_flow, const float* feat_nhwc, const float* init_feat_nchw, int init_feat_div, int mode,
+                    float* A, __nv_bfloat16* A16, int lda, int N, int n_hyp, cudaStream_t st) {
+  DVD_REQUIRE(init_flow && feat_nhwc && (A || A16) && lda >= 1032 && lda % 4 == 0 && n_hyp > 0 && init_feat_div > 0, "build_r: bad args");
+  k_build_r<<<N * 1024, 256, 0, st>>>(init_flow, feat_nhwc, init_feat_nchw, init_feat_div, mode, A, A16, lda, n_hyp);
+  DVD_LAUNCH_CHECK("k_build_r");
+  return 0;
+}
+
+__global__ void k_obs_embed(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                            const float* __restrict__ pos, float* __restrict__ out, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int j = i % kHid; size_t row = i / kHid;
+  int w = row % 32, h = (row / 32) % 32; size_t n = row / 1024;
+  const float* p = x + n * 2 * 4096 + (2 * h) * 64 + 2 * w;
+  const float* wr = W + (size_t)j * 8;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const float* q = p + c * 4096;
+    acc += __ldg(wr + c * 4 + 0) * __ldg(q) + __ldg(wr + c * 4 + 1) * __ldg(q + 1) + __ldg(wr + c * 4 + 2) * __ldg(q + 64) +
+           __ldg(wr + c * 4 + 3) * __ldg(q + 65);
+  }
+  out[i] = acc + __ldg(bias + j) + __ldg(pos + (row % 1024) * kHid + j);
+}
+int obs_embed(const float* x, const float* W, const float* bias, const float* pos, float* out, int N, cudaStream_t st) {
+  DVD_REQUIRE(x && W && bias && pos && out, "obs_embed: null");
+  size_t total = (size_t)N * 1024 * kHid;
+  k_obs_embed<<<cdiv(total, 256), 256, 0, st>>>(x, W, bias, pos, out, total);
+  DVD_LAUNCH_CHECK("k_obs_embed");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ softmax
+template <int NV>   // float4 per lane, n = 128*NV
+__global__ void __launch_bounds__(256) k_softmax(float* __restrict__ S, long long rows) {
+  long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4* p = reinterpret_cast<float4*>(S + row * (128 * NV));
+  float4 v[NV];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { v[i] = p[lane + 32 * i]; m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w))); }
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x = expf(v[i].x - m); v[i].y = expf(v[i].y - m); v[i].z = expf(v[i].z - m); v[i].w = expf(v[i].w - m);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float inv = 1.0f / warp_sum(s);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) p[lane + 32 * i] = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+}
+int softmax_rows(float* S, long long rows, int n, cudaStream_t st) {
+  DVD_REQUIRE(S && rows > 0 && n % 128 == 0 && n <= 1024, "softmax_rows: n must be a multiple of 128 <= 1024 (got %d)", n);
+  dim3 grid(cdiv(rows, 8));
+  switch (n / 128) {
+    case 1: k_softmax<1><<<grid, 256, 0, st>>>(S, rows); break;
+    case 2: k_softmax<2><<<grid, 256, 0, st>>>(S, rows); break;
+    case 4: k_softmax<4><<<grid, 256, 0, st>>>(S, rows); break;
+    case 8: k_softmax<8><<<grid, 256, 0, st>>>(S, rows); break;
+    default: set_error("softmax_rows: unsupported n=%d", n); return DVD_E_BADARG;
+  }
+  DVD_LAUNCH_CHECK("k_softmax");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ small dense layers
+constexpr int GEMV_MAXR = 8;
+__global__ void __launch_bounds__(256) k_gemv(const float* __restrict__ in, int ldin, const float* __restrict__ W,
+                                              const float* __restrict__ b, float* __restrict__ out, int ldo, int rows, int N,
+                                              int K, int silu_in, int in_mod, int act) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= N) return;
+  float acc[GEMV_MAXR];
+#pragma unroll
+  for (int r = 0; r < GEMV_MAXR; ++r) acc[r] = 0.f;
+  const float* wr = W + (size_t)j * K;
+  for (int k = lane; k < K; k += 32) {
+    float wv = __ldg(wr + k);
+    int ki = in_mod > 0 ? (k % in_mod) : k;
+#pragma unroll
+    for (int r = 0; r < GEMV_MAXR; ++r) {
+      if (r < rows) {
+        float x = __ldg(in + (size_t)r * ldin + ki);
+        if (silu_in) x = silu(x);
+        acc[r] = fmaf(wv, x, acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < GEMV_MAXR; ++r) {
+    if (r < rows) {
+      float v = warp_sum(acc[r]);
+      if (lane == 0) {
+        if (b) v += __ldg(b + j);
+        if (act == 1) v = fmaxf(v, 0.f);
+        else if (act == 3) v = sigmoidf_(v);
+        else if (act == 4) v = silu(v);
+        out[(size_t)r * ldo + j] = v;
+      }
+    }
+  }
+}
+int gemv(const float* in, int ldin, const float* W, const float* b, float* out, int ldo, int rows, int N, int K, int silu_in,
+         int in_mod, int act, cudaStream_t st) {
+  DVD_REQUIRE(in && W && out && N > 0 && K > 0, "gemv: bad args");
+  for (int r0 = 0; r0 < rows; r0 += GEMV_MAXR) {
+    int nr = rows - r0 < GEMV_MAXR ? rows - r0 : GEMV_MAXR;
+    k_gemv<<<cdiv(N, 8), 256, 0, st>>>(in + (size_t)r0 * ldin, ldin, W, b, out + (size_t)r0 * ldo, ldo, nr, N, K, silu_in, in_mod, act);
+    DVD_LAUNCH_CHECK("k_gemv");
+  }
+  return 0;
+}
+
+__global__ void k_timestep_embedding(const float* __restrict__ t, float* __restrict__ out, int rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 128) return;
+  int r = i / 128, k = i % 128;
+  // CM:123-129: freqs = exp(-ln(10000) * k / 128) in fp32 ; args = t * freqs ; cat(cos, sin)
+  float f = expf(-9.210340371976184f * (float)k / 128.0f);
+  float a = t[r] * f;
+  out[r * 256 + k] = cosf(a);
+  out[r * 256 + 128 + k] = sinf(a);
+}
+int timestep_embedding(const float* t, float* out, int rows, cudaStream_t st) {
+  k_timestep_embedding<<<cdiv(rows * 128, 128), 128, 0, st>>>(t, out, rows);
+  DVD_LAUNCH_CHECK("k_timestep_embedding");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ decoder positional encoding
+// deterministic two-stage mean: 32 token chunks of 32, then a fixed-order finish
+__global__ void __launch_bounds__(128) k_token_partial(const float* __restrict__ X, float* __restrict__ part, int C) {
+  const int c = blockIdx.x * 128 + threadIdx.x, chunk = blockIdx.y, n = blockIdx.z;
+  if (c >= C) return;
+  const float* p = X + ((size_t)n * 1024 + chunk * 32) * C + c;
+  float s = 0.f;
+#pragma unroll 8
+  for (int t = 0; t < 32; ++t) s += __ldg(p + (size_t)t * C);
+  part[((size_t)n * 32 + chunk) * C + c] = s;
+}
+__global__ void k_token_finish(const float* __restrict__ part, float* __restrict__ out, int C, int total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int n = i / C, c = i % C;
+  float s = 0.f;
+  for (int k = 0; k < 32; ++k) s += part[((size_t)n * 32 + k) * C + c];
+  out[i] = s * (1.0f / 1024.0f);
+}
+int token_mean(const float* X, float* out, int N, int C, cudaStream_t st) {
+  // `out` must have room for N*C results followed by N*32*C partials
+  DVD_REQUIRE(X && out, "token_mean: null");
+  float* part = out + (size_t)N * C;
+  k_token_partial<<<dim3(cdiv(C, 128), 32, N), 128, 0, st>>>(X, part, C);
+  DVD_LAUNCH_CHECK("k_token_partial");
+  k_token_finish<<<cdiv(N * C, 256), 256, 0, st>>>(part, out, C, N * C);
+  DVD_LAUNCH_CHECK("k_token_finish");
+  return 0;
+}
+
+__global__ void k_posenc_add(float4* __restrict__ X, const float4* __restrict__ hs, const float4* __restrict__ ws,
+                             const float4* __restrict__ hpe, const float4* __restrict__ wpe, int C4, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = i % C4; size_t row = i / C4;
+  int tok = row % 1024; size_t n = row / 1024;
+  float4 x = X[i], a = __ldg(hs + n * C4 + c), b = __ldg(ws + n * C4 + c);
+  float4 hp = __ldg(hpe + (size_t)(tok / 32) * C4 + c), wp = __ldg(wpe + (size_t)(tok % 32) * C4 + c);
+  // CA:153: out = x + h_pos_encoding + w_pos_encoding (left to right)
+  x.x = (x.x + a.x * hp.x) + b.x * wp.x; x.y = (x.y + a.y * hp.y) + b.y * wp.y;
+  x.z = (x.z + a.z * hp.z) + b.z * wp.z; x.w = (x.w + a.w * hp.w) + b.w * wp.w;
+  X[i] = x;
+}
+int posenc_add(float* X, const float* hs, const float* ws, const float* hpe, const float* wpe, int N, int C, cudaStream_t st) {
+  DVD_REQUIRE(X && hs && ws && hpe && wpe && C % 4 == 0, "posenc_add: bad args");
+  size_t total = (size_t)N * 1024 * (C / 4);
+  k_posenc_add<<<cdiv(total, 256), 256, 0, st>>>((float4*)X, (const float4*)hs, (const float4*)ws, (const float4*)hpe,
+                                                 (const float4*)wpe, C / 4, total);
+  DVD_LAUNCH_CHECK("k_posenc_add");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ depthwise 3x3
+__global__ void __launch_bounds__(256) k_dwconv(const float4* __restrict__ in, const float4* __restrict__ w9, const float4* __restrict__ sc,
+                                                const float4* __restrict__ sh, float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
+                                                int C4, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = i % C4; size_t row = i / C4;
+  int tok = row % 1024; size_t n = row / 1024;
+  int y = tok / 32, x = tok % 32;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    int yy = y + ky - 1;
+    if (yy < 0 || yy >= 32) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      int xx = x + kx - 1;
+      if (xx < 0 || xx >= 32) continue;
+      float4 v = __ldg(in + (n * 1024 + yy * 32 + xx) * C4 + c), ww = __ldg(w9 + (size_t)(ky * 3 + kx) * C4 + c);
+      acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y); acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+    }
+  }
+  float4 s = __ldg(sc + c), t = __ldg(sh + c);
+  float r0 = fmaxf(acc.x * s.x + t.x, 0.f), r1 = fmaxf(acc.y * s.y + t.y, 0.f), r2 = fmaxf(acc.z * s.z + t.z, 0.f), r3 = fmaxf(acc.w * s.w + t.w, 0.f);
+  store4(out, out16, i * 4, r0, r1, r2, r3);
+}
+int dwconv3x3_bn_relu(const float* in, const float* w9c, const float* scale, const float* shift, float* out, __nv_bfloat16* out16,
+                      int N, int C, cudaStream_t st) {
+  DVD_REQUIRE(in && w9c && scale && shift && (out || out16) && C % 4 == 0, "dwconv: bad args");
+  size_t total = (size_t)N * 1024 * (C / 4);
+  k_dwconv<<<cdiv(total, 256), 256, 0, st>>>((const float4*)in, (const float4*)w9c, (const float4*)scale, (const float4*)shift, out, out16,
+                                             C / 4, total);
+  DVD_LAUNCH_CHECK("k_dwconv");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ final layer + DDIM update
+__global__ void __launch_bounds__(256) k_final(const float* __restrict__ X, const float* __restrict__ lw, const float* __restrict__ lb,
+                                               const float* __restrict__ shift, const float* __restrict__ scale,
+                                               const float* __restrict__ W8, const float* __restrict__ b8,
+                                               const float* __restrict__ init_flow, const float* __restrict__ x_t, float a, float b,
+                                               float* __restrict__ pred, float* __restrict__ x_prev, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  constexpr int NV = 12, C = 1536;
+  const float4* x4 = reinterpret_cast<const float4*>(X + (size_t)row * C);
+  float v[NV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float4 t = __ldg(x4 + lane + 32 * i);
+    v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+    s += (t.x + t.y) + (t.z + t.w);
+  }
+  float mean = warp_sum(s) * (1.0f / C), q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float d = v[i][j] - mean; q += d * d; }
+  float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);            // decoder.layer_norm, CA:457
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (lane + 32 * i) * 4;
+    float4 ww = __ldg(reinterpret_cast<const float4*>(lw + c0)), bb = __ldg(reinterpret_cast<const float4*>(lb + c0));
+    v[i][0] = (v[i][0] - mean) * rstd * ww.x + bb.x; v[i][1] = (v[i][1] - mean) * rstd * ww.y + bb.y;
+    v[i][2] = (v[i][2] - mean) * rstd * ww.z + bb.z; v[i][3] = (v[i][3] - mean) * rstd * ww.w + bb.w;
+    s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+  }
+  mean = warp_sum(s) * (1.0f / C); q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float d = v[i][j] - mean; q += d * d; }
+  rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + 1e-6f);                  // norm_final, CM:321,334
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (lane + 32 * i) * 4;
+    float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c0)), sh = __ldg(reinterpret_cast<const float4*>(shift + c0));
+    float y0 = (v[i][0] - mean) * rstd * (1.f + sc.x) + sh.x, y1 = (v[i][1] - mean) * rstd * (1.f + sc.y) + sh.y;
+    float y2 = (v[i][2] - mean) * rstd * (1.f + sc.z) + sh.z, y3 = (v[i][3] - mean) * rstd * (1.f + sc.w) + sh.w;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float4 w = __ldg(reinterpret_cast<const float4*>(W8 + (size_t)o * C + c0));
+      acc[o] += (y0 * w.x + y1 * w.y) + (y2 * w.z + y3 * w.w);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = warp_sum(acc[o]);
+  if (lane < 8) {
+    float val = 0.f;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) if (lane == o) val = acc[o];
+    const int o = lane;
+    val += __ldg(b8 + o);
+    // CM:563-565 unpatchify 'nhwpqc->nchpwq': o = p*4 + q*2 + c
+    const int p = o >> 2, qq = (o >> 1) & 1, c = o & 1;
+    const int tok = row % 1024, n = row / 1024, h = tok / 32, w = tok % 32;
+    const size_t idx = ((size_t)(n * 2 + c) * 64 + 2 * h + p) * 64 + 2 * w + qq;
+    const float pr = val + __ldg(init_flow + idx);                         // CM:645-646
+    pred[idx] = pr;
+    if (x_prev) x_prev[idx] = a * pr + b * __ldg(x_t + idx);              // GD:470-489 with eta = 0
+  }
+}
+int final_layer(const float* X, const float* ln_w, const float* ln_b, const float* shift, const float* scale, const float* W8,
+                const float* b8, const float* init_flow, const float* x_t, float a, float b, float* pred, float* x_prev, int N,
+                cudaStream_t st) {
+  DVD_REQUIRE(X && ln_w && ln_b && shift && scale && W8 && b8 && init_flow && pred && (x_t || !x_prev), "final_layer: null");
+  k_final<<<cdiv(N * 1024, 8), 256, 0, st>>>(X, ln_w, ln_b, shift, scale, W8, b8, init_flow, x_t, a, b, pred, x_prev, N * 1024);
+  DVD_LAUNCH_CHECK("k_final");
+  return 0;
+}
+
+__global__ void k_hyp_mean_clamp(const float* __restrict__ pred, float* __restrict__ out, int n_hyp, int total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int d = i / 8192, e = i % 8192;
+  float s = 0.f;
+  for (int h = 0; h < n_hyp; ++h) s += pred[((size_t)d * n_hyp + h) * 8192 + e];
+  out[i] = fminf(fmaxf(s / (float)n_hyp, -1.f), 1.f);
+}
+int hyp_mean_clamp(const float* pred, float* out, int docs, int n_hyp, cudaStream_t st) {
+  DVD_REQUIRE(pred && out && n_hyp > 0, "hyp_mean_clamp: bad args");
+  if (docs == 0) return 0;
+  k_hyp_mean_clamp<<<cdiv(docs * 8192, 256), 256, 0, st>>>(pred, out, n_hyp, docs * 8192);
+  DVD_LAUNCH_CHECK("k_hyp_mean_clamp");
+  return 0;
+}
+
+__global__ void k_f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st) {
+  k_f32_to_bf16<<<cdiv(n, 256), 256, 0, st>>>(in, out, n);
+  DVD_LAUNCH_CHECK("k_f32_to_bf16");
+  return 0;
+}
+
+}  // namespace dvd
+namespace dvd {
+__global__ void k_bf16_to_f32(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+int bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st) {
+  k_bf16_to_f32<<<cdiv(n, 256), 256, 0, st>>>(in, out, n);
+  DVD_LAUNCH_CHECK("k_bf16_to_f32");
+  return 0;
+}
+}  // namespace dvd

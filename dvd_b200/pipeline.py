@@ -1,0 +1,129 @@
+"""The call a user makes: photo(s) + conditioning in, dewarped image(s) out.
+
+``DewarpPipeline`` is the hot part of the reference's per-document loop
+(train_settings/dvd/evaluation.py:245-268 sampling, :300-306 upsample/affine, :317-318 unwarp) for
+a fixed batch of ``docs`` documents per call.  Everything between the inputs and the dewarped
+image runs in libdvd_b200; torch only owns the buffers and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+import torch
+
+from . import _lib
+from .model import DiT
+from .sampler import create_gaussian_diffusion
+from .unwarp import AFFINE
+
+
+class DewarpPipeline:
+    def __init__(self, model: DiT, diffusion_steps: int = 3, n_batch: int = 2, docs: int = 1, height: int = 1500, width: int = 2000,
+                 noise_schedule: str = "cosine"):
+        self.model, self.docs, self.n_batch, self.H, self.W = model, docs, n_batch, height, width
+        self.dev = model.device
+        if self.dev.type != "cuda":
+            raise RuntimeError("DewarpPipeline needs the model on a CUDA device (no CPU path)")
+        self.diffusion = create_gaussian_diffusion(steps=diffusion_steps, noise_schedule=noise_schedule, predict_xstart=True,
+                                                   rescale_timesteps=True, rescale_learned_sigmas=True, timestep_respacing="")
+        self.lib = _lib.lib()
+        with torch.cuda.device(self.dev):
+            self.eng = model.engine(docs, n_batch)
+            self.t_scaled, t_emb, self.a, self.b = self.diffusion._plan()
+            self.tables = self.eng.tables(t_emb)
+            z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=self.dev)
+            self.buf = {"y512": z(docs, 3, 512, 512), "mask_cat": z(docs, 1, 512, 512), "mask_y512": z(docs, 384, 64, 64),
+                        "line_msk": z(docs, 64, 64, 64), "x_T": z(docs * n_batch, 2, 64, 64),
+                        "photo_u8": z(docs, height, width, 3, dt=torch.uint8)}
+            self.init_flow0 = z(docs, 2, 64, 64)                       # evaluation.py:180 (use_init_flow=False)
+            self.map64 = z(docs, 2, 64, 64)
+            self.out_u8 = z(docs, height, width, 3, dt=torch.uint8)
+            self.out_host = torch.empty((docs, height, width, 3), dtype=torch.uint8).pin_memory()
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.buf.values())
+        self.d2h_bytes = self.out_u8.numel()
+
+    # ---- device-resident inputs: dict with y512, mask_cat, mask_y512, line_msk, x_T, photo_u8 (all on self.dev)
+    def run_device(self, d: dict) -> torch.Tensor:
+        with torch.cuda.device(self.dev):
+            st = _lib.stream_ptr()
+            self.eng.static_forward(d["y512"], d["mask_cat"], d["mask_y512"], d["line_msk"])
+            self.eng.sample(d["x_T"], self.init_flow0, self.tables, self.t_scaled, self.a, self.b, None, self.map64)
+            _lib.check(self.lib.dvd_unwarp_u8(_lib.ptr(d["photo_u8"]), _lib.ptr(self.map64), _lib.ptr(self.out_u8), self.docs, 3,
+                                              self.H, self.W, 64, 64, AFFINE, st), "dvd_unwarp_u8")
+        return self.out_u8
+
+    # ---- pinned-host inputs -> host uint8 image (H2D and D2H inside the call)
+    def run_host(self, h: dict) -> torch.Tensor:
+        with torch.cuda.device(self.dev):
+            for k, v in self.buf.items():
+                v.copy_(h[k], non_blocking=True)
+            self.run_device(self.buf)
+            self.out_host.copy_(self.out_u8, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return self.out_host
+
+    # ---- measurement helpers used by bench.py
+    def profile_kernels(self, d: dict, iters: int = 5) -> dict:
+        """CUDA-event timing (on the launch stream, L2 flushed between runs) of the kernel classes inside a real step, and of
+        the unwarp kernel; returns the roofline objects of the bench JSON line."""
+        peaks_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+        try:
+            peaks = json.load(open(peaks_path)); which = "measured"
+        except Exception:
+            peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}; which = "fallback"
+        with torch.cuda.device(self.dev):
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+            ms, fl, ln = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)()
+            tot_ms, tot = [0.0, 0.0, 0.0], 0.0
+            for it in range(iters):
+                flush.fill_(it)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self.lib.dvd_profile_begin()
+                e0.record()
+                self.eng.static_forward(d["y512"], d["mask_cat"], d["mask_y512"], d["line_msk"])
+                self.eng.sample(d["x_T"], self.init_flow0, self.tables, self.t_scaled, self.a, self.b, None, self.map64)
+                e1.record()
+                _lib.check(self.lib.dvd_profile_end(ms, fl, ln), "dvd_profile_end")
+                if it == 0:
+                    continue                                        # warm-up
+                tot += e0.elapsed_time(e1)
+                for c in range(3):
+                    tot_ms[c] += ms[c]
+            n = iters - 1
+            share = {"gemm": tot_ms[0] / tot, "attention": tot_ms[1] / tot, "pyramid_conv": tot_ms[2] / tot,
+                     "other": 1.0 - sum(tot_ms) / tot, "denoiser_ms_per_step": tot / n}
+            gemm_tf = fl[0] / (tot_ms[0] / n * 1e-3) / 1e12 if tot_ms[0] > 0 else 0.0
+            attn_tf = fl[1] / (tot_ms[1] / n * 1e-3) / 1e12 if tot_ms[1] > 0 else 0.0
+            tensor_mode = self.model.precision == "bf16"
+            peak_tf = peaks["bf16_tflops_sustained"] if tensor_mode else 72.0      # fp32 FFMA: 148 SM x 128 FMA x 2 x 1.9 GHz
+            roof = {"kernel": "dense GEMM (all linear layers of one step batch)", "bound": "tensor", "achieved": gemm_tf,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": None,
+                    "launches_per_step": int(ln[0]), "gflop_per_step": fl[0] / 1e9, "attention_tflops": attn_tf,
+                    "attention_gflop_per_step": fl[1] / 1e9,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % which) if tensor_mode else "nominal fp32 FFMA"}
+            # unwarp: fp32 contract (24 B/px) and the uint8 variant actually used end to end (6 B/px)
+            photo_f = d["photo_u8"].permute(0, 3, 1, 2).float().contiguous()
+            out_f = torch.empty_like(photo_f)
+            px = self.docs * self.H * self.W
+
+            def time_unwarp(fn):
+                ts = []
+                for it in range(iters + 2):
+                    flush.fill_(it)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); fn(); e1.record(); e1.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                return sum(ts[2:]) / len(ts[2:])
+            st = _lib.stream_ptr()
+            t32 = time_unwarp(lambda: self.lib.dvd_unwarp_f32(_lib.ptr(photo_f), _lib.ptr(self.map64), _lib.ptr(out_f), self.docs, 3, self.H,
+                                                              self.W, 64, 64, AFFINE, st))
+            t8 = time_unwarp(lambda: self.lib.dvd_unwarp_u8(_lib.ptr(d["photo_u8"]), _lib.ptr(self.map64), _lib.ptr(self.out_u8), self.docs, 3,
+                                                            self.H, self.W, 64, 64, AFFINE, st))
+            gb32, gb8 = 24.0 * px / 1e9, 6.0 * px / 1e9
+            ru = {"kernel": "k_unwarp fp32 NCHW (24 B/px)", "bound": "hbm", "achieved": gb32 / (t32 * 1e-3), "peak": peaks["hbm_gbs"],
+                  "unit": "GB/s", "frac": gb32 / (t32 * 1e-3) / peaks["hbm_gbs"], "traffic": None, "ms": t32,
+                  "u8_variant": {"achieved": gb8 / (t8 * 1e-3), "frac": gb8 / (t8 * 1e-3) / peaks["hbm_gbs"], "ms": t8, "bytes_per_px": 6},
+                  "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % which}
+        return {"roofline": roof, "roofline_unwarp": ru, "share": share}

@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path (through the C-ABI library) against the CPU oracle and the golden
+fixtures produced by the unmodified reference.  Run on the B200 box with ``-m gpu``.
+
+Tolerances (north_star): final backward map within 0.05 px mean / 0.5 px max in fp32 mode, i.e.
+2.48e-5 / 2.48e-4 in normalised units at the largest named size (4032 px: px = d * (4032-1)/2);
+bf16 mode: <= 1.5e-3 mean / 6e-3 max normalised (the reference itself moves by
+9.5e-4 / 2.7e-3 when its GEMM operands are rounded to bf16); unwarped image PSNR >= 45 dB.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dvd_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+FP32_MEAN, FP32_MAX = 0.05 / 2015.5, 0.5 / 2015.5
+BF16_MEAN, BF16_MAX = 1.5e-3, 6e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from dvd_b200 import _lib
+    _lib.check(_lib.lib().dvd_check_device(), "dvd_check_device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def models(dev, state_dict_live):
+    from dvd_b200.model import DiT
+    out = {}
+    for prec in ("fp32", "bf16"):
+        m = DiT(precision=prec)
+        m.load_state_dict(state_dict_live, strict=False)
+        out[prec] = m.to(dev).eval()
+    return out
+
+
+def _diffusion(S=3):
+    from dvd_b200.sampler import create_gaussian_diffusion
+    return create_gaussian_diffusion(steps=S, noise_schedule="cosine", predict_xstart=True, rescale_timesteps=True,
+                                     rescale_learned_sigmas=True, timestep_respacing="")
+
+
+def _kwargs(inp):
+    return {"init_flow": inp["init_flow"], "src_feat": None, "src_64": None, "y512": inp["y512"], "tmode": "stage_1_dit_cross",
+            "mask_cat": inp["mask_cat"], "init_feat": inp["init_feat"], "iter": True, "mask_y512": inp["mask_y512"],
+            "line_msk": inp["line_msk"]}
+
+
+def _sample(model, inp, S=3):
+    out, final = _diffusion(S).ddim_sample_loop(model, (inp["y512"].shape[0], 2, 64, 64), clip_denoised=False, model_kwargs=_kwargs(inp),
+                                                eta=0.0, n_batch=2, time_variant=True, x_T=inp["x_T"])
+    torch.cuda.synchronize()
+    return out.cpu(), final
+
+
+def psnr(a, b, peak=255.0):
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return 99.0 if mse == 0 else 10 * np.log10(peak * peak / mse)
+
+
+# ----------------------------------------------------------------------------------------------- unwarp (K11)
+UNWARP_CASES = {"sampled_page": None, "smooth_noise": (0, "smooth", 120, 90, 12, "noise"),
+                "adversarial_noise": (1, "adversarial", 64, 200, 13, "noise"), "zero_page_1ch": (2, "zero", 77, 131, 14, "page")}
+
+
+def _unwarp_case(golden_dir, case):
+    if case == "sampled_page":
+        g3 = np.load(os.path.join(golden_dir, "sample_S3_doc0.npz"))
+        return torch.from_numpy(g3["sample"]), synth.make_photo(96, 128, 11, "page")
+    mid, mkind, H, W, seed, pkind = UNWARP_CASES[case]
+    photo = synth.make_photo(H, W, seed, pkind)
+    if case == "zero_page_1ch":
+        photo = photo[:, :1].contiguous()
+    return synth.make_map64(mid, mkind), photo
+
+
+@pytest.mark.parametrize("case", list(UNWARP_CASES))
+def test_unwarp_matches_reference_golden(dev, golden_dir, case):
+    from dvd_b200 import dewarp_fullres, fullres_grid
+    u = np.load(os.path.join(golden_dir, "unwarp.npz"))
+    m, photo = _unwarp_case(golden_dir, case)
+    H, W = photo.shape[-2:]
+    grid = fullres_grid(m.to(dev), H, W).cpu()
+    gd = (grid - torch.from_numpy(u[case + "_grid"])).abs()
+    # grid error in pixels of the photo
+    assert float(gd[:, 0].max()) * (W - 1) / 2 < 2e-3 and float(gd[:, 1].max()) * (H - 1) / 2 < 2e-3
+    img = dewarp_fullres(m.to(dev), photo.to(dev)).cpu()
+    ref = torch.from_numpy(u[case + "_img"])
+    assert psnr(img, ref) >= 60.0, psnr(img, ref)
+    u8 = dewarp_fullres(m.to(dev), photo.to(dev), out_uint8=True).cpu().numpy()[0]
+    assert (u8 != u[case + "_u8"]).mean() < 5e-3                      # a rare +-1 LSB at truncation boundaries
+    assert np.abs(u8.astype(int) - u[case + "_u8"].astype(int)).max() <= 1
+    # uint8-in / uint8-out variant == fp32 variant truncated (photo values are integers)
+    pu8 = photo[0].permute(1, 2, 0).to(torch.uint8).unsqueeze(0).contiguous().to(dev)
+    u8b = dewarp_fullres(m.to(dev), pu8).cpu().numpy()[0]
+    assert np.array_equal(u8b, u8)
+
+
+@pytest.mark.parametrize("H,W", [(1500, 2000), (4032, 3024)])
+def test_unwarp_fullsize_vs_oracle(dev, H, W):
+    """BASELINE configs' photo sizes: PSNR >= 45 dB against the oracle chain (EV:300-306 + grid_sample)."""
+    from dvd_b200 import dewarp_fullres
+    m = synth.make_map64(5, "smooth")
+    photo = synth.make_photo(H, W, 21, "page")
+    img = dewarp_fullres(m.to(dev), photo.to(dev)).cpu()
+    ref = O.unwarp(m, photo)
+    assert psnr(img, ref) >= 45.0
+    assert float((img - ref).abs().max()) < 1.0
+
+
+def test_unwarp_properties_and_edges(dev):
+    from dvd_b200 import dewarp_fullres, register_model2
+    # linearity in the photo: unwarp(a*p1 + p2) == a*unwarp(p1) + unwarp(p2)
+    m = synth.make_map64(7, "smooth").to(dev)
+    p1, p2 = synth.make_photo(300, 500, 1, "noise").to(dev), synth.make_photo(300, 500, 2, "page").to(dev)
+    lhs = dewarp_fullres(m, 0.5 * p1 + p2)
+    rhs = 0.5 * dewarp_fullres(m, p1) + dewarp_fullres(m, p2)
+    assert float((lhs - rhs).abs().max()) < 1e-3
+    # constant photo: inside pixels stay constant, zero padding only lowers values
+    const = torch.full((1, 3, 200, 300), 200.0, device=dev)
+    o = dewarp_fullres(torch.zeros(1, 2, 64, 64, device=dev), const)
+    assert float(o.max()) <= 200.0 + 1e-3 and float(o[:, :, 5:-5, 5:-5].min()) >= 200.0 - 1e-3
+    # batch of photos == one at a time; ragged sizes (W not a multiple of 4, single row / column)
+    for (H, W) in [(33, 61), (1, 17), (19, 1), (2, 2)]:
+        ph = synth.make_photo(H, W, 3, "noise")
+        mm = synth.make_map64(3, "adversarial")
+        got = dewarp_fullres(mm.to(dev), ph.to(dev)).cpu()
+        assert psnr(got, O.unwarp(mm, ph)) >= 60.0, (H, W)
+    two_m = torch.cat([synth.make_map64(1, "smooth"), synth.make_map64(2, "smooth")]).to(dev)
+    two_p = torch.cat([synth.make_photo(64, 96, 4, "noise"), synth.make_photo(64, 96, 5, "noise")]).to(dev)
+    both = dewarp_fullres(two_m, two_p)
+    for i in range(2):
+        assert torch.equal(both[i:i + 1], dewarp_fullres(two_m[i:i + 1], two_p[i:i + 1]))
+    # empty batch is a no-op
+    assert dewarp_fullres(torch.zeros(0, 2, 64, 64, device=dev), torch.zeros(0, 3, 8, 8, device=dev)).shape[0] == 0
+    # reg_model_bilin drop-in (WP:14-23) vs torch grid_sample semantics restated in the oracle
+    reg = register_model2((512, 512), "bilinear")
+    img = torch.rand(2, 5, 40, 50)
+    grid = torch.rand(2, 2, 30, 20) * 2.4 - 1.2
+    assert float((reg([img.to(dev), grid.to(dev)]).cpu() - O.grid_sample_ref(img, grid)).abs().max()) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- building blocks
+def _run_gemm(dev, M, N, K, prec):
+    from dvd_b200 import _lib
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    Ad, Wd, bd = A.to(dev), W.to(dev), b.to(dev)
+    Cd = torch.empty(M, N, device=dev)
+    scratch = torch.empty((M + N) * K * 2 + 1024, dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().dvd_test_gemm(_lib.ptr(Ad), _lib.ptr(Wd), _lib.ptr(bd), _lib.ptr(Cd), M, N, K, prec, _lib.ptr(scratch),
+                                        scratch.numel(), _lib.stream_ptr()), "dvd_test_gemm")
+    torch.cuda.synchronize()
+    return Cd.cpu(), A, W, b
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 1032), (2048, 1536, 384), (384, 64, 36), (130, 72, 100)])
+def test_gemm_fp32(dev, M, N, K):
+    Cg, A, W, b = _run_gemm(dev, M, N, K, 0)
+    ref = (A.double() @ W.double().t() + b.double()).float()
+    assert float((Cg - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 1032), (2048, 1536, 384), (8192, 1152, 384), (2048, 4608, 1536),
+                                   (2048, 384, 1536)])
+def test_gemm_bf16_tcgen05(dev, M, N, K):
+    Cg, A, W, b = _run_gemm(dev, M, N, K, 1)
+    ref = (A.bfloat16().double() @ W.bfloat16().double().t() + b.double()).float()     # same operand rounding, exact accumulate
+    assert float((Cg - ref).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+def _run_attn(dev, B, H, T, d, prec):
+    from dvd_b200 import _lib
+    g = torch.Generator().manual_seed(B + H + d)
+    q, k, v = (torch.randn(B, T, H * d, generator=g) for _ in range(3))
+    o = torch.empty(B, T, H * d, device=dev)
+    scratch = torch.empty(max(B * H * T * T * 4, B * T * H * d * 12) + 1024, dtype=torch.uint8, device=dev)
+    qd, kd, vd = q.to(dev), k.to(dev), v.to(dev)
+    _lib.check(_lib.lib().dvd_test_attention(_lib.ptr(qd), _lib.ptr(kd), _lib.ptr(vd), _lib.ptr(o), B, H, T, d, d ** -0.5, prec,
+                                             _lib.ptr(scratch), scratch.numel(), _lib.stream_ptr()), "dvd_test_attention")
+    torch.cuda.synchronize()
+    return o.cpu(), q, k, v
+
+
+@pytest.mark.parametrize("d", [64, 256])
+def test_attention_fp32(dev, d):
+    o, q, k, v = _run_attn(dev, 2, 6, 1024, d, 0)
+    ref = O._mha_core(q, k, v, 6, d ** -0.5)
+    assert float((o - ref).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("d", [64, 256])
+def test_attention_bf16_tcgen05(dev, d):
+    o, q, k, v = _run_attn(dev, 2, 6, 1024, d, 1)
+    ref = O._mha_core(q.bfloat16().float(), k.bfloat16().float(), v.bfloat16().float(), 6, d ** -0.5)
+    assert float((o - ref).abs().max()) < 2e-2 and float((o - ref).abs().mean()) < 2e-3
+
+
+# ----------------------------------------------------------------------------------------------- denoiser stages
+def test_static_forward_and_first_step_fp32(dev, models, state_dict_live, golden_dir):
+    sd, model = state_dict_live, models["fp32"]
+    inp = synth.make_doc_inputs(0, H=96, W=128)
+    st = np.load(os.path.join(golden_dir, "stages_doc0_step0.npz"))
+    g3 = np.load(os.path.join(golden_dir, "sample_S3_doc0.npz"))
+    eng = model.engine(1, 2)
+    g = lambda k: inp[k].to(dev).contiguous()
+    eng.static_forward(g("y512"), g("mask_cat"), g("mask_y512"), g("line_msk"))
+    feat = eng.feat_nhwc().permute(0, 3, 1, 2).cpu()
+    np.testing.assert_allclose(feat[:, ::16, ::4, ::4].numpy(), g3["feat_sub"][:1], atol=5e-5, rtol=1e-4)
+    pos = sd["noised_obs_pos_embed"]
+    for name, key in (("cond", "c_embed"), ("msk6", "m_embed"), ("msk_line", "l_embed")):
+        got = eng.tensor(name).view(1, 1024, 384).cpu() - pos
+        np.testing.assert_allclose(got[:, ::8, ::8].numpy(), st[key][:1], atol=1e-4, rtol=1e-4)
+    tab = eng.tables([2.0])
+    np.testing.assert_allclose(tab[0, :384].cpu().numpy(), st["t_emb"][0], atol=2e-6)
+    pred = torch.empty(2, 2, 64, 64, device=dev)
+    eng.denoise_step(inp["x_T"].to(dev), torch.zeros(2, 2, 64, 64, device=dev), None, True, tab[0], 1.0, 0.0, pred, None)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose((eng.tensor("r").view(2, 1024, 384).cpu() - pos)[:, ::8, ::8].numpy(), st["r_embed"], atol=1e-4, rtol=1e-4)
+    np.testing.assert_allclose((eng.tensor("xe").view(2, 1024, 384).cpu() - pos)[:, ::8, ::8].numpy(), st["obs_embed"], atol=1e-5, rtol=1e-4)
+    assert float((pred.cpu() - torch.from_numpy(g3["pred"][0])).abs().max()) < 1e-4
+
+
+def test_dropin_model_call_matches_reference(dev, models, golden_dir):
+    """model(x, t, **kwargs) with the reference's kwargs (cross_model.py:568-570), second step (explicit init_feat)."""
+    g3 = np.load(os.path.join(golden_dir, "sample_S3_doc0.npz"))
+    inp = synth.make_doc_inputs(0, H=96, W=128)
+    rep = lambda v: v.repeat(2, 1, 1, 1).to(dev)
+    x = torch.from_numpy(g3["x"][0]).to(dev)
+    out, feat = models["fp32"](x, torch.tensor([2, 2], device=dev).float() * (1000.0 / 3), init_flow=rep(inp["init_flow"]),
+                               init_feat=rep(inp["init_feat"]), y512=rep(inp["y512"]), mask_cat=rep(inp["mask_cat"]),
+                               mask_y512=rep(inp["mask_y512"]), line_msk=rep(inp["line_msk"]), tmode="stage_1_dit_cross", iter=True, tv=True)
+    assert tuple(out.shape) == (2, 2, 64, 64) and tuple(feat.shape) == (2, 256, 64, 64)
+    assert float((out.cpu() - torch.from_numpy(g3["pred"][0])).abs().max()) < 1e-4
+    np.testing.assert_allclose(feat.cpu()[:, ::16, ::4, ::4].numpy(), g3["feat_sub"], atol=5e-5, rtol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------- end to end
+@pytest.mark.parametrize("doc", [0, 1])
+def test_sampling_fp32_matches_reference_golden(dev, models, golden_dir, doc):
+    g = np.load(os.path.join(golden_dir, f"sample_S3_doc{doc}.npz"))
+    out, final = _sample(models["fp32"], synth.make_doc_inputs(doc, H=96, W=128))
+    d = (out - torch.from_numpy(g["sample"])).abs()
+    assert float(d.mean()) < FP32_MEAN and float(d.max()) < FP32_MAX, (float(d.mean()) * 2015.5, float(d.max()) * 2015.5)
+    assert tuple(final["feat_dict"].shape) == (1, 256, 64, 64) and final["sample"] is final["pred_xstart"]
+
+
+@pytest.mark.parametrize("doc", [0, 1])
+def test_sampling_bf16_within_stated_bound(dev, models, golden_dir, doc):
+    g = np.load(os.path.join(golden_dir, f"sample_S3_doc{doc}.npz"))
+    out, _ = _sample(models["bf16"], synth.make_doc_inputs(doc, H=96, W=128))
+    d = (out - torch.from_numpy(g["sample"])).abs()
+    assert float(d.mean()) < BF16_MEAN and float(d.max()) < BF16_MAX, (float(d.mean()), float(d.max()))
+
+
+def test_sampling_S10_thresholds_fp32(dev, models, golden_dir):
+    """S = 10 hits t = 600.0 and 300.0 exactly (strict thresholds of cross_model.py:576-579)."""
+    g = np.load(os.path.join(golden_dir, "sample_S10_doc2.npz"))
+    out, _ = _sample(models["fp32"], synth.make_doc_inputs(2, H=96, W=128), S=10)
+    assert float((out - torch.from_numpy(g["sample"])).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_document_batch_equals_single_documents(dev, models, prec):
+    """Documents are independent: a batch of 3 documents gives the same maps as three separate calls."""
+    inps = [synth.make_doc_inputs(d, with_photo=False) for d in (0, 1, 5)]
+    cat = {k: torch.cat([i[k] for i in inps]) for k in inps[0]}
+    both, _ = _sample(models[prec], cat)
+    for j, i in enumerate(inps):
+        one, _ = _sample(models[prec], i)
+        assert float((both[j:j + 1] - one).abs().max()) < (1e-5 if prec == "fp32" else 1e-3)
+
+
+def test_seeded_noise_consumption_matches_reference_order(dev, models):
+    """Without x_T the sampler draws randn(shape) then randn(n_batch, ...) like gaussian_diffusion.py:559-569."""
+    inp = synth.make_doc_inputs(0, with_photo=False)
+    torch.manual_seed(123); torch.cuda.manual_seed(123)
+    _ = torch.randn(1, 2, 64, 64, device=dev); xT = torch.randn(2, 2, 64, 64, device=dev)
+    torch.manual_seed(123); torch.cuda.manual_seed(123)
+    a, _ = _diffusion().ddim_sample_loop(models["fp32"], (1, 2, 64, 64), clip_denoised=False, model_kwargs=_kwargs(inp), eta=0.0,
+                                         n_batch=2, time_variant=True)
+    b, _ = _diffusion().ddim_sample_loop(models["fp32"], (1, 2, 64, 64), clip_denoised=False, model_kwargs=_kwargs(inp), eta=0.0,
+                                         n_batch=2, time_variant=True, x_T=xT)
+    assert torch.equal(a, b)
+
+
+def test_end_to_end_dewarp_psnr(dev, models, golden_dir):
+    """Sampling (fp32 mode) + unwarp of a 1500x2000 photo vs oracle unwarp of the reference's golden map: PSNR >= 45 dB."""
+    from dvd_b200 import dewarp_fullres
+    g = np.load(os.path.join(golden_dir, "sample_S3_doc0.npz"))
+    inp = synth.make_doc_inputs(0, H=96, W=128)
+    out, _ = _sample(models["fp32"], inp)
+    photo = synth.make_photo(1500, 2000, 77, "page")
+    img = dewarp_fullres(out.to(dev), photo.to(dev)).cpu()
+    ref = O.unwarp(torch.from_numpy(g["sample"]), photo)
+    assert psnr(img, ref) >= 45.0, psnr(img, ref)
