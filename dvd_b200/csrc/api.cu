@@ -91,11 +91,13 @@ extern "C" int dvd_test_attention(const float* q, const float* k, const float* v
     return gemm_f32(g, A_DIRECT, B_KN, batch * heads, st);
   }
   size_t n = (size_t)batch * T * ld;
-  DVD_REQUIRE(scratch_bytes >= n * 2 * 4 + 4 * n, "test_attention: scratch needs %zu bytes", n * 12);
+  DVD_REQUIRE(scratch_bytes >= n * 2 * 5, "test_attention: scratch needs %zu bytes", n * 10);
   __nv_bfloat16* q16 = (__nv_bfloat16*)scratch; __nv_bfloat16* k16 = q16 + n; __nv_bfloat16* v16 = k16 + n; __nv_bfloat16* o16 = v16 + n;
+  __nv_bfloat16* vt16 = o16 + n;
   int rc = f32_to_bf16(q, q16, n, st); if (rc) return rc;
   rc = f32_to_bf16(k, k16, n, st); if (rc) return rc;
   rc = f32_to_bf16(v, v16, n, st); if (rc) return rc;
-  rc = attention_tc_bf16(q16, ld, k16, ld, v16, ld, o16, ld, batch, heads, T, d, scale, 1, st); if (rc) return rc;
+  rc = transpose_v_bf16(v16, ld, vt16, batch, T, ld, st); if (rc) return rc;
+  rc = attention_tc_bf16(q16, ld, k16, ld, vt16, o16, ld, batch, heads, T, d, scale, 1, st); if (rc) return rc;
   return bf16_to_f32(o16, o, n, st);
 }

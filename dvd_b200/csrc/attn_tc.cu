@@ -1,0 +1,256 @@
+// Fused attention on tcgen05: O = softmax(scale * Q K^T) V for one (sample, head, 128-query tile) per CTA.
+//
+//   S = Q K^T  : UMMA M=128 (queries) x N=64 (keys) x K=d, accumulator in TMEM (two S buffers)
+//   softmax    : 4 warps, one query row per thread (TMEM lane == row): tcgen05.ld S, online max / exp2 / sum in fp32,
+//                P (bf16) written to shared memory in the 128-byte-swizzled K-major layout the next MMA reads
+//   O += P V   : UMMA M=128 x N=d x K=64, accumulator stays resident in TMEM for the whole KV sweep; it is rescaled
+//                in place (tcgen05.ld / tcgen05.st) only when a row maximum grows by more than 2^8 (lazy rescale)
+//   epilogue   : O / rowsum -> bf16 -> global
+// All three operands are K-major: Q [T, d], K [T, d] and V^T [d, T] (the QKV GEMM epilogue writes V transposed), so the
+// same SWIZZLE_128B TMA boxes + UMMA descriptors as the GEMM are used.  Warp roles: 0 = TMA producer, 1 = MMA issuer,
+// 2..5 = softmax/correction/epilogue.  d in {64, 256}; T a multiple of 128.
+#include "gemm_tc.cuh"
+#include "tc_common.cuh"
+
+namespace dvd {
+using namespace tc;
+
+constexpr int AQ = 128;      // queries per CTA
+constexpr int AKV = 64;      // keys per pipeline step
+
+template <int D>
+struct AttnCfg {
+  static constexpr int STAGES = (D == 64) ? 4 : 2;
+  static constexpr int Q_BYTES = AQ * D * 2;
+  static constexpr int K_BYTES = AKV * D * 2, V_BYTES = D * AKV * 2;
+  static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
+  static constexpr int P_BYTES = AQ * AKV * 2;
+  static constexpr int SMEM = Q_BYTES + STAGES * STAGE_BYTES + P_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;      // 2 x 64 (S) + D (O), rounded to a power of two
+  static constexpr int O_COL = 2 * AKV;
+};
+
+template <int D>
+__global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                 const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ O, int ldo, int T,
+                                                 int heads, int kv_div, float scale_log2) {
+  using Cfg = AttnCfg<D>;
+  constexpr int ST = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Cfg::Q_BYTES;
+  uint8_t* sP = sKV + ST * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // ST
+  uint64_t* kv_empty = kv_full + ST;       // ST
+  uint64_t* s_full = kv_empty + ST;        // 2
+  uint64_t* s_empty = s_full + 2;          // 2
+  uint64_t* p_full = s_empty + 2;          // 1
+  uint64_t* pv_done = p_full + 1;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AQ, h = blockIdx.y, n = blockIdx.z, nkv = n / kv_div;
+  const int nt = T / AKV;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmVt);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 128); }
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: Q once, then the K / V^T ring
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int j = 0; j < D / 64; ++j) tma_load_2d(sQ + j * (AQ * 128), &tmQ, q_full, h * D + 64 * j, n * T + q0);
+      for (int t = 0; t < nt; ++t) {
+        const int s = t % ST, u = t / ST;
+        mbar_wait(&kv_empty[s], (u & 1) ^ 1);
+        uint8_t* k = sKV + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&kv_full[s], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < D / 64; ++j) tma_load_2d(k + j * (AKV * 128), &tmK, &kv_full[s], h * D + 64 * j, nkv * T + t * AKV);
+        tma_load_2d(k + Cfg::K_BYTES, &tmVt, &kv_full[s], t * AKV, (nkv * heads + h) * D);     // box: 64 keys x D rows of V^T
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer
+      constexpr uint32_t idesc_qk = make_idesc_bf16(AQ, AKV);     // 128 x 64
+      constexpr uint32_t idesc_pv = make_idesc_bf16(AQ, D);       // 128 x D
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      auto issue_qk = [&](int t) {
+        const int s = t % ST, b = t & 1;
+        mbar_wait(&kv_full[s], (t / ST) & 1);
+        mbar_wait(&s_empty[b], ((t >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t k_addr = smem_u32(sKV + s * Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          mma_f16_ss(tmem_base + b * AKV, make_desc_k_sw128(q_addr + (k >> 2) * (AQ * 128) + (k & 3) * 32),
+                     make_desc_k_sw128(k_addr + (k >> 2) * (AKV * 128) + (k & 3) * 32), idesc_qk, k ? 1u : 0u);
+        mma_commit(&s_full[b]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int t = 0; t < nt; ++t) {
+        if (t + 1 < nt) issue_qk(t + 1);                          // S(t+1) overlaps softmax(t)
+        mbar_wait(p_full, t & 1);
+        fence_after_sync();
+        const uint32_t v_addr = smem_u32(sKV + (t % ST) * Cfg::STAGE_BYTES + Cfg::K_BYTES);
+#pragma unroll
+        for (int k = 0; k < AKV / 16; ++k)
+          mma_f16_ss(tmem_base + Cfg::O_COL, make_desc_k_sw128(p_addr + k * 32), make_desc_k_sw128(v_addr + k * 32), idesc_pv,
+                     (t | k) ? 1u : 0u);
+        mma_commit(&kv_empty[t % ST]);                            // K and V^T of this stage are free
+        mma_commit(pv_done);                                      // P buffer free, O(t) complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax / correction / epilogue: thread <-> query row (TMEM lane)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    for (int t = 0; t < nt; ++t) {
+      const int b = t & 1;
+      mbar_wait(&s_full[b], (t >> 1) & 1);
+      fence_after_sync();
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32(lane_base + b * AKV, s0);
+      tmem_ld_32x32(lane_base + b * AKV + 32, s1);
+      tmem_ld_wait();
+      fence_before_sync();
+      mbar_arrive(&s_empty[b]);                                   // S(b) is in registers: the next QK^T may overwrite it
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[j]), __uint_as_float(s1[j])));
+      const float m_new = fmaxf(m, mx * scale_log2);
+      // lazy rescale: keep the stale maximum while exp2 stays below 2^8 (exact after the final division by l)
+      const bool grow = (m_new - m) > 8.0f;                       // also true for t == 0 (m = -inf)
+      const float alpha = (grow && t > 0) ? exp2f(m - m_new) : 1.0f;
+      if (grow) m = m_new;
+      float sum = 0.f;
+      uint32_t pk[32];                                            // 64 bf16 probabilities, packed in pairs
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float a0 = exp2f(fmaf(__uint_as_float(s0[j]), scale_log2, -m)), a1 = exp2f(fmaf(__uint_as_float(s0[j + 1]), scale_log2, -m));
+        float b0 = exp2f(fmaf(__uint_as_float(s1[j]), scale_log2, -m)), b1 = exp2f(fmaf(__uint_as_float(s1[j + 1]), scale_log2, -m));
+        __nv_bfloat162 pa = __floats2bfloat162_rn(a0, a1), pb = __floats2bfloat162_rn(b0, b1);
+        // the row sum uses the same bf16-rounded values the tensor core multiplies with
+        sum += (__low2float(pa) + __high2float(pa)) + (__low2float(pb) + __high2float(pb));
+        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&pa);
+        pk[16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&pb);
+      }
+      l = l * alpha + sum;
+      if (t > 0) {
+        mbar_wait(pv_done, (t - 1) & 1);                          // PV(t-1) finished: P buffer reusable, O readable
+        fence_after_sync();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {             // warp-uniform: tcgen05.ld/st are warp-collective
+#pragma unroll 1
+          for (int c = 0; c < D; c += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32(lane_base + Cfg::O_COL + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st_32x32(lane_base + Cfg::O_COL + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
+      uint8_t* prow = sP + row * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = v;
+      }
+      fence_proxy_async();                                        // generic-proxy writes -> visible to the UMMA (async proxy)
+      fence_before_sync();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue
+    mbar_wait(pv_done, (nt - 1) & 1);
+    fence_after_sync();
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = O + (size_t)(n * T + q0 + row) * ldo + h * D;
+#pragma unroll 1
+    for (int c = 0; c < D; c += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32(lane_base + Cfg::O_COL + c, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
+        u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+        u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(orow + c + j) = u;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// V [nsamp, T, C] (row stride ldv) -> V^T [nsamp, C, T]; only used by the test hook (the denoiser's GEMM epilogue writes V^T directly)
+__global__ void k_transpose_v(const __nv_bfloat16* __restrict__ v, int ldv, __nv_bfloat16* __restrict__ vt, int T, int C) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int n = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) tile[r][threadIdx.x] = v[((size_t)n * T + t0 + r) * ldv + c0 + threadIdx.x];
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) vt[((size_t)n * C + c0 + r) * T + t0 + threadIdx.x] = tile[threadIdx.x][r];
+}
+int transpose_v_bf16(const __nv_bfloat16* v, int ldv, __nv_bfloat16* vt, int nsamp, int T, int C, cudaStream_t st) {
+  DVD_REQUIRE(v && vt && T % 32 == 0 && C % 32 == 0, "transpose_v: bad args");
+  k_transpose_v<<<dim3(T / 32, C / 32, nsamp), dim3(32, 8), 0, st>>>(v, ldv, vt, T, C);
+  DVD_LAUNCH_CHECK("k_transpose_v");
+  return 0;
+}
+
+int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt, __nv_bfloat16* o, int ldo,
+                      int nsamp, int heads, int T, int d, float scale, int kv_div, cudaStream_t st) {
+  DVD_REQUIRE(q && k && vt && o, "attention_tc: null pointer");
+  DVD_REQUIRE((d == 64 || d == 256) && T % 128 == 0 && nsamp > 0 && kv_div > 0 && nsamp % kv_div == 0, "attention_tc: bad shape d=%d T=%d", d, T);
+  DVD_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention_tc: output must be 16-byte aligned");
+  const int nkv = nsamp / kv_div;
+  CUtensorMap tmQ, tmK, tmVt;
+  int rc = make_tmap_bf16_2d(&tmQ, q, (uint64_t)nsamp * T, (uint64_t)heads * d, (uint64_t)ldq, AQ, 64); if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmK, k, (uint64_t)nkv * T, (uint64_t)heads * d, (uint64_t)ldk, AKV, 64); if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmVt, vt, (uint64_t)nkv * heads * d, (uint64_t)T, (uint64_t)T, d, 64); if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DVD_CUDA(cudaFuncSetAttribute(k_attn_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::SMEM));
+    DVD_CUDA(cudaFuncSetAttribute(k_attn_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<256>::SMEM));
+    attr_set = true;
+  }
+  const float scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(T / AQ, heads, nsamp);
+  if (d == 64) k_attn_tc<64><<<grid, 192, AttnCfg<64>::SMEM, st>>>(tmQ, tmK, tmVt, o, ldo, T, heads, kv_div, scale_log2);
+  else         k_attn_tc<256><<<grid, 192, AttnCfg<256>::SMEM, st>>>(tmQ, tmK, tmVt, o, ldo, T, heads, kv_div, scale_log2);
+  DVD_LAUNCH_CHECK("k_attn_tc");
+  return 0;
+}
+
+}  // namespace dvd

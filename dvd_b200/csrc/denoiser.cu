@@ -24,7 +24,8 @@ struct Workspace {
   float *flow[2], *xbuf[2], *pred;
   // bf16 operand staging (DVD_PREC_BF16)
   __nv_bfloat16 *a_stat16, *ctx16[3], *a_r16, *r16, *qn16, *xo16, *hmod16, *h116, *hd16, *att_d16, *f216;
-  __nv_bfloat16 *q16, *kv_static16[3], *kv_r16, *qkv16, *qkv_d16;       // attention operands
+  __nv_bfloat16 *q16, *kv_static16[3], *kv_r16, *qkv16, *qkv_d16;       // attention operands (Q, K row-major)
+  __nv_bfloat16 *vt_static16[3], *vt_r16, *vt_qkv16, *vt_d16;            // V^T [sample, C_v, 1024] written by the GEMM epilogues
   size_t s_floats;
   size_t total_bytes;
 };
@@ -69,6 +70,8 @@ static Workspace carve(void* base, int docs, int n_hyp, int precision) {
     w.h116 = H(4 * M * 1536); w.hd16 = H(M * 1536); w.att_d16 = H(M * 1536); w.f216 = H(M * 2048);
     w.q16 = H(M * 384); w.kv_r16 = H(M * 768); w.qkv16 = H(4 * M * 1152); w.qkv_d16 = H(M * 4608);
     for (int i = 0; i < 3; ++i) w.kv_static16[i] = H(Md * 768);
+    for (int i = 0; i < 3; ++i) w.vt_static16[i] = H(Md * 384);
+    w.vt_r16 = H(M * 384); w.vt_qkv16 = H(4 * M * 384); w.vt_d16 = H(M * 1536);
   }
   w.total_bytes = off;
   return w;
@@ -191,16 +194,17 @@ static int static_forward(const Ctx& c, const float* y512, const float* mask_cat
     // ---- static cross-attention K,V (in_proj rows 384..1151)
     Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = s.kv_static[i]; ek.ldc = 768;
     ek.out_bf16 = c.tc() ? s.kv_static16[i] : nullptr; ek.ldc_bf16 = 768;
+    if (c.tc()) { ek.vt_out = s.vt_static16[i]; ek.vt_col0 = 384; }
     DVD_TRY(linear(c, s.ctx[i], s.ctx16[i], 384, w.xattn_in, 384, Md, 768, ek));
   }
   return 0;
 }
 
 static int attention(const Ctx& c, const float* q, const __nv_bfloat16* q16, int ldq, const float* k, const __nv_bfloat16* k16, int ldk,
-                     const float* v, const __nv_bfloat16* v16, int ldv, float* o, __nv_bfloat16* o16, int ldo, int nsamp, int d,
+                     const float* v, const __nv_bfloat16* vt16, int ldv, float* o, __nv_bfloat16* o16, int ldo, int nsamp, int d,
                      float scale, int kv_div) {
   ProfScope ps(PC_ATTN, c.st, 4.0 * nsamp * kHeads * 1024.0 * 1024.0 * d);
-  if (c.tc()) return attention_tc_bf16(q16, ldq, k16, ldk, v16, ldv, o16, ldo, nsamp, kHeads, 1024, d, scale, kv_div, c.st);
+  if (c.tc()) return attention_tc_bf16(q16, ldq, k16, ldk, vt16, o16, ldo, nsamp, kHeads, 1024, d, scale, kv_div, c.st);
   return attention_f32(q, ldq, k, ldk, v, ldv, o, ldo, nsamp, kHeads, 1024, d, scale, kv_div, c.ws.S, c.ws.s_floats, c.st);
 }
 
@@ -227,12 +231,14 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     Epilogue e; e.bias = w.xattn_in_b; e.out = s.q; e.ldc = 384; e.out_bf16 = tc ? s.q16 : nullptr; e.ldc_bf16 = 384;
     DVD_TRY(linear(c, s.qn, s.qn16, 384, w.xattn_in, 0, M, 384, e));
     Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = s.kv_r; ek.ldc = 768; ek.out_bf16 = tc ? s.kv_r16 : nullptr; ek.ldc_bf16 = 768;
+    if (tc) { ek.vt_out = s.vt_r16; ek.vt_col0 = 384; }
     DVD_TRY(linear(c, s.r, s.r16, 384, w.xattn_in, 384, M, 768, ek));
   }
   for (int i = 0; i < 4; ++i) {                  // stream order x1..x4 = cond, msk6, msk_line, r  (CM:243-265)
     const float* kv = i < 3 ? s.kv_static[i] : s.kv_r;
     const __nv_bfloat16* kv16 = tc ? (i < 3 ? s.kv_static16[i] : s.kv_r16) : nullptr;
-    DVD_TRY(attention(c, s.q, s.q16, 384, kv, kv16, 768, kv + 384, tc ? kv16 + 384 : nullptr, 768, s.xo + (size_t)i * M * 384,
+    const __nv_bfloat16* vt16 = tc ? (i < 3 ? s.vt_static16[i] : s.vt_r16) : nullptr;
+    DVD_TRY(attention(c, s.q, s.q16, 384, kv, kv16, 768, kv + 384, vt16, 768, s.xo + (size_t)i * M * 384,
                       tc ? s.xo16 + (size_t)i * M * 384 : nullptr, 384, N, 64, 0.125f, i < 3 ? c.n_hyp : 1));
   }
   {
@@ -244,10 +250,10 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
                     ada + 384, st));
   {
     Epilogue e; e.bias = w.blk_qkv_b; e.out = s.qkv; e.ldc = 1152; e.out_bf16 = tc ? s.qkv16 : nullptr; e.ldc_bf16 = 1152;
-    if (tc) e.out = nullptr;
+    if (tc) { e.out = nullptr; e.vt_out = s.vt_qkv16; e.vt_col0 = 768; }
     DVD_TRY(linear(c, s.hmod, s.hmod16, 384, w.blk_qkv, 0, 4 * M, 1152, e));
   }
-  DVD_TRY(attention(c, s.qkv, s.qkv16, 1152, s.qkv + 384, tc ? s.qkv16 + 384 : nullptr, 1152, s.qkv + 768, tc ? s.qkv16 + 768 : nullptr, 1152,
+  DVD_TRY(attention(c, s.qkv, s.qkv16, 1152, s.qkv + 384, tc ? s.qkv16 + 384 : nullptr, 1152, s.qkv + 768, s.vt_qkv16, 1152,
                     s.xo, s.xo16, 384, 4 * N, 64, 0.125f, 1));
   {
     Epilogue e; e.bias = w.blk_proj_b; e.gate = ada + 768; e.resid = s.xs; e.ldr = 384; e.out = s.xs; e.ldc = 384;
@@ -281,10 +287,11 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, tc ? s.hd16 : nullptr, 1536, M, 1536, 1e-5f, L.n1_w, L.n1_b, nullptr, nullptr, st));
     {
       Epilogue e; e.out = tc ? nullptr : s.qkv_d; e.ldc = 4608; e.out_bf16 = tc ? s.qkv_d16 : nullptr; e.ldc_bf16 = 4608;
+      if (tc) { e.vt_out = s.vt_d16; e.vt_col0 = 3072; }
       DVD_TRY(linear(c, s.hd, s.hd16, 1536, L.qkv, 0, M, 4608, e));
     }
-    DVD_TRY(attention(c, s.qkv_d, s.qkv_d16, 4608, s.qkv_d + 1536, tc ? s.qkv_d16 + 1536 : nullptr, 4608, s.qkv_d + 3072,
-                      tc ? s.qkv_d16 + 3072 : nullptr, 4608, s.att_d, s.att_d16, 1536, N, 256, 0.0625f, 1));
+    DVD_TRY(attention(c, s.qkv_d, s.qkv_d16, 4608, s.qkv_d + 1536, tc ? s.qkv_d16 + 1536 : nullptr, 4608, s.qkv_d + 3072, s.vt_d16, 4608,
+                      s.att_d, s.att_d16, 1536, N, 256, 0.0625f, 1));
     {
       Epilogue e; e.resid = s.X; e.ldr = 1536; e.out = s.X; e.ldc = 1536;
       DVD_TRY(linear(c, s.att_d, s.att_d16, 1536, L.fc, 0, M, 1536, e));

@@ -30,6 +30,10 @@ struct Epilogue {
   int group_col_stride = 0;           //               out col += (row / group_rows) * group_col_stride
   __nv_bfloat16* out_bf16 = nullptr;  // optional bf16 copy of the output (same mapping, ld = ldc_bf16)
   int ldc_bf16 = 0;
+  // tensor path only: columns >= vt_col0 (the V projection) are ALSO written transposed for the attention kernel:
+  //   vt_out[(row / 1024) * (N - vt_col0) + (col - vt_col0)][row % 1024]      i.e. V^T [sample, C_v, T = 1024]
+  __nv_bfloat16* vt_out = nullptr;
+  int vt_col0 = 0;
 };
 
 __device__ __forceinline__ float apply_epilogue(const Epilogue& e, float v, int row, int col, int N) {

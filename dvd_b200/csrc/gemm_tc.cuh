@@ -10,9 +10,13 @@ int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ld
                  cudaStream_t st);
 
 // softmax(scale * Q K^T) V per (sample, head); bf16 in/out, fp32 softmax statistics and accumulation.
-// q/k/v/o row-major with leading dims ld*, head h at columns [h*d, (h+1)*d); k/v of sample n come
-// from sample n / kv_div.  d in {64, 256}, T multiple of 128.
-int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
-                      __nv_bfloat16* o, int ldo, int nsamp, int heads, int T, int d, float scale, int kv_div, cudaStream_t st);
+// q/k/o row-major with leading dims ld*, head h at columns [h*d, (h+1)*d); vt is V TRANSPOSED: [nsamp/kv_div, heads*d, T]
+// (written by the QKV GEMM epilogue, Epilogue::vt_out).  k/vt of sample n come from sample n / kv_div.
+// d in {64, 256}, T multiple of 128.
+int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt, __nv_bfloat16* o, int ldo,
+                      int nsamp, int heads, int T, int d, float scale, int kv_div, cudaStream_t st);
+
+// V [nsamp, T, C] (row stride ldv) -> V^T [nsamp, C, T]  (test hook only)
+int transpose_v_bf16(const __nv_bfloat16* v, int ldv, __nv_bfloat16* vt, int nsamp, int T, int C, cudaStream_t st);
 
 }  // namespace dvd

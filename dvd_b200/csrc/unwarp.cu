@@ -195,9 +195,9 @@ __global__ void k_grid_sample(const float* __restrict__ img, const float* __rest
 template <int IN_U8, int OUT_U8>
 static int launch_unwarp(const void* photo, const float* map, void* out, int B, int C, int H, int W, int mh, int mw,
                          float affine, cudaStream_t st) {
-  DVD_REQUIRE(photo && map && out, "unwarp: null pointer");
   DVD_REQUIRE(B >= 0 && H >= 0 && W >= 0 && mh >= 1 && mw >= 1 && C >= 1 && C <= 4, "unwarp: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
-  if (B == 0 || H == 0 || W == 0) return 0;
+  if (B == 0 || H == 0 || W == 0) return 0;          // empty batch / empty photo: nothing to do
+  DVD_REQUIRE(photo && map && out, "unwarp: null pointer");
   DVD_REQUIRE(B <= 65535 && cdiv(H, TILE_H) <= 65535, "unwarp: grid too large");
   UnwarpGeom g = make_geom(H, W, mh, mw, affine);
   dim3 grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B), block(32, 8);
