@@ -208,7 +208,7 @@ def run_ours(a):
             fn(i)
         barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        lib.dvd_launch_count(1)
+        pipe.kernel_launches = 0
         t0 = time.perf_counter()
         for i in range(steps):
             flush.fill_(i & 0xFF)                                             # L2 flush between timed iterations (not timed)
@@ -217,7 +217,7 @@ def run_ours(a):
             evs[i][1].record()
         barrier()
         wall = time.perf_counter() - t0
-        launches = lib.dvd_launch_count(1)
+        launches = pipe.kernel_launches
         ms = [s.elapsed_time(e) for s, e in evs]
         return ms, wall, launches
 
@@ -253,7 +253,7 @@ def run_ours(a):
                 "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
                 "config": {"workload": workload_name(a), "docs_per_step_per_gpu": a.docs, "photo_hw": [a.height, a.width],
                            "diffusion_steps": a.diffusion_steps, "n_batch": a.n_batch, "weights": "random-init (oracle/synth.py seed 1234)",
-                           "l2": "256 MiB flush write between timed iterations", "parallelism": f"document-sharded x{world}, no collective"},
+                           "l2": "256 MiB flush write between timed iterations", "cuda_graph": pipe.use_graph, "parallelism": f"document-sharded x{world}, no collective"},
                 "p50_latency_ms": statistics.median(ms_dev),
                 "e2e": {"value": e2e, "unit": "docs/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                         "p50_latency_ms": statistics.median(ms_e2e), "io": "uint8 HWC photo in, uint8 HWC dewarped image out"},

@@ -157,7 +157,7 @@ static int linear(const Ctx& c, const float* A32, const __nv_bfloat16* A16, int 
 #define DVD_TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 static int conv3x3(const Ctx& c, const float* in, float* out, int B, int H, int W, int Cin, const dvd_mat_t& Wt, const float* bias) {
-  // TODO(tensor path): implicit-GEMM on tcgen05 with TMA im2col boxes; the pyramid runs once per document.
+  // fp32 mode: implicit GEMM on the FFMA path
   ProfScope ps(PC_CONV, c.st, 2.0 * B * H * W * Wt.n * 9.0 * Cin);
   GemmParams p;
   p.A = in; p.convH = H; p.convW = W; p.convC = Cin;
@@ -171,16 +171,46 @@ static int static_forward(const Ctx& c, const float* y512, const float* mask_cat
   const int B = c.docs, Md = B * 1024;
   // ---- K1 pyramid (CM:83-95): 7 x conv3x3+ReLU, 3 x maxpool, NHWC
   DVD_TRY(pack_y4(y512, mask_cat, s.y4, B, st));
-  DVD_TRY(conv3x3(c, s.y4, s.pyrP, B, 512, 512, 4, w.pyr[0], w.pyr_b[0]));
-  DVD_TRY(conv3x3(c, s.pyrP, s.pyrQ, B, 512, 512, 64, w.pyr[1], w.pyr_b[1]));
-  DVD_TRY(maxpool2_nhwc(s.pyrQ, s.pyrP, B, 512, 512, 64, st));
-  DVD_TRY(conv3x3(c, s.pyrP, s.pyrQ, B, 256, 256, 64, w.pyr[2], w.pyr_b[2]));
-  DVD_TRY(conv3x3(c, s.pyrQ, s.pyrP, B, 256, 256, 128, w.pyr[3], w.pyr_b[3]));
-  DVD_TRY(maxpool2_nhwc(s.pyrP, s.pyrQ, B, 256, 256, 128, st));
-  DVD_TRY(conv3x3(c, s.pyrQ, s.pyrP, B, 128, 128, 128, w.pyr[4], w.pyr_b[4]));
-  DVD_TRY(conv3x3(c, s.pyrP, s.pyrQ, B, 128, 128, 256, w.pyr[5], w.pyr_b[5]));
-  DVD_TRY(conv3x3(c, s.pyrQ, s.pyrP, B, 128, 128, 256, w.pyr[6], w.pyr_b[6]));
-  DVD_TRY(maxpool2_nhwc(s.pyrP, s.feat, B, 128, 128, 256, st));
+  if (c.tc()) {
+    // level_0 (Cin = 4, K = 36) stays on the FFMA path and emits bf16 NHWC; the six wide convs run as implicit GEMMs on
+    // tcgen05 with bf16 activations; the last pool writes the fp32 feature map the rest of the model consumes.
+    __nv_bfloat16 *P = (__nv_bfloat16*)s.pyrP, *Q = (__nv_bfloat16*)s.pyrQ;
+    {
+      ProfScope ps(PC_CONV, st, 2.0 * B * 512 * 512 * 64 * 36.0);
+      GemmParams p;
+      p.A = s.y4; p.convH = 512; p.convW = 512; p.convC = 4;
+      p.B = w.pyr[0].f32; p.ldb = 36; p.M = B * 512 * 512; p.N = 64; p.K = 36;
+      p.e.bias = w.pyr_b[0]; p.e.act = ACT_RELU; p.e.out_bf16 = P; p.e.ldc_bf16 = 64;
+      DVD_TRY(gemm_f32(p, A_CONV3, B_NK, 1, st));
+    }
+    auto conv = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int H, int Cin, int layer) -> int {
+      const int Cout = w.pyr[layer].n;
+      ProfScope ps(PC_CONV, st, 2.0 * B * H * H * Cout * 9.0 * Cin);
+      Epilogue e; e.bias = w.pyr_b[layer]; e.act = ACT_RELU; e.out_bf16 = out; e.ldc_bf16 = Cout;
+      DVD_REQUIRE(w.pyr[layer].bf16, "pyramid bf16 weights missing");
+      return conv3x3_tc_bf16(in, (const __nv_bfloat16*)w.pyr[layer].bf16, B, H, H, Cin, Cout, e, st);
+    };
+    DVD_TRY(conv(P, Q, 512, 64, 1));
+    DVD_TRY(maxpool2_nhwc_bf16(Q, P, nullptr, B, 512, 512, 64, st));
+    DVD_TRY(conv(P, Q, 256, 64, 2));
+    DVD_TRY(conv(Q, P, 256, 128, 3));
+    DVD_TRY(maxpool2_nhwc_bf16(P, Q, nullptr, B, 256, 256, 128, st));
+    DVD_TRY(conv(Q, P, 128, 128, 4));
+    DVD_TRY(conv(P, Q, 128, 256, 5));
+    DVD_TRY(conv(Q, P, 128, 256, 6));
+    DVD_TRY(maxpool2_nhwc_bf16(P, nullptr, s.feat, B, 128, 128, 256, st));
+  } else {
+    DVD_TRY(conv3x3(c, s.y4, s.pyrP, B, 512, 512, 4, w.pyr[0], w.pyr_b[0]));
+    DVD_TRY(conv3x3(c, s.pyrP, s.pyrQ, B, 512, 512, 64, w.pyr[1], w.pyr_b[1]));
+    DVD_TRY(maxpool2_nhwc(s.pyrQ, s.pyrP, B, 512, 512, 64, st));
+    DVD_TRY(conv3x3(c, s.pyrP, s.pyrQ, B, 256, 256, 64, w.pyr[2], w.pyr_b[2]));
+    DVD_TRY(conv3x3(c, s.pyrQ, s.pyrP, B, 256, 256, 128, w.pyr[3], w.pyr_b[3]));
+    DVD_TRY(maxpool2_nhwc(s.pyrP, s.pyrQ, B, 256, 256, 128, st));
+    DVD_TRY(conv3x3(c, s.pyrQ, s.pyrP, B, 128, 128, 128, w.pyr[4], w.pyr_b[4]));
+    DVD_TRY(conv3x3(c, s.pyrP, s.pyrQ, B, 128, 128, 256, w.pyr[5], w.pyr_b[5]));
+    DVD_TRY(conv3x3(c, s.pyrQ, s.pyrP, B, 128, 128, 256, w.pyr[6], w.pyr_b[6]));
+    DVD_TRY(maxpool2_nhwc(s.pyrP, s.feat, B, 128, 128, 256, st));
+  }
   // ---- K2 static patch embeds (c: CM:594, m: CM:585, l: CM:605), + bias + pos
   Epilogue e; e.pos = w.pos; e.pos_rows = 1024;
   for (int i = 0; i < 3; ++i) {
@@ -188,11 +218,11 @@ static int static_forward(const Ctx& c, const float* y512, const float* mask_cat
     const int C = i == 0 ? 256 : (i == 1 ? 384 : 64);
     if (i == 0) DVD_TRY(patchify_nhwc(s.feat, c.tc() ? nullptr : s.a_stat, c.tc() ? s.a_stat16 : nullptr, 4 * C, B, C, st));
     else DVD_TRY(patchify_nchw(i == 1 ? mask_y512 : line_msk, c.tc() ? nullptr : s.a_stat, c.tc() ? s.a_stat16 : nullptr, 4 * C, B, C, st));
-    Epilogue ee = e; ee.bias = w.emb_b[emb]; ee.out = s.ctx[i]; ee.ldc = 384;
+    Epilogue ee = e; ee.bias = w.emb_b[emb]; ee.out = c.tc() ? nullptr : s.ctx[i]; ee.ldc = 384;
     ee.out_bf16 = c.tc() ? s.ctx16[i] : nullptr; ee.ldc_bf16 = 384;
     DVD_TRY(linear(c, s.a_stat, s.a_stat16, 4 * C, w.emb[emb], 0, Md, 384, ee));
     // ---- static cross-attention K,V (in_proj rows 384..1151)
-    Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = s.kv_static[i]; ek.ldc = 768;
+    Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = c.tc() ? nullptr : s.kv_static[i]; ek.ldc = 768;
     ek.out_bf16 = c.tc() ? s.kv_static16[i] : nullptr; ek.ldc_bf16 = 768;
     if (c.tc()) { ek.vt_out = s.vt_static16[i]; ek.vt_col0 = 384; }
     DVD_TRY(linear(c, s.ctx[i], s.ctx16[i], 384, w.xattn_in, 384, Md, 768, ek));
@@ -221,16 +251,16 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
   DVD_TRY(build_r_operand(init_flow, s.feat, init_feat_nchw, init_feat_div, feat_mode, tc ? nullptr : s.a_r, tc ? s.a_r16 : nullptr,
                           lda_r, N, c.n_hyp, st));
   {
-    Epilogue e; e.bias = w.emb_b[1]; e.pos = w.pos; e.pos_rows = 1024; e.out = s.r; e.ldc = 384;
+    Epilogue e; e.bias = w.emb_b[1]; e.pos = w.pos; e.pos_rows = 1024; e.out = tc ? nullptr : s.r; e.ldc = 384;
     e.out_bf16 = tc ? s.r16 : nullptr; e.ldc_bf16 = 384;
     DVD_TRY(linear(c, s.a_r, s.a_r16, lda_r, w.emb[1], 0, M, 384, e));
   }
   // ---- cross attention (CM:237-265): one shared query, four contexts
   DVD_TRY(layernorm(s.xe, 384, tc ? nullptr : s.qn, 384, tc ? s.qn16 : nullptr, 384, M, 384, 1e-6f, nullptr, nullptr, nullptr, nullptr, st));
   {
-    Epilogue e; e.bias = w.xattn_in_b; e.out = s.q; e.ldc = 384; e.out_bf16 = tc ? s.q16 : nullptr; e.ldc_bf16 = 384;
+    Epilogue e; e.bias = w.xattn_in_b; e.out = tc ? nullptr : s.q; e.ldc = 384; e.out_bf16 = tc ? s.q16 : nullptr; e.ldc_bf16 = 384;
     DVD_TRY(linear(c, s.qn, s.qn16, 384, w.xattn_in, 0, M, 384, e));
-    Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = s.kv_r; ek.ldc = 768; ek.out_bf16 = tc ? s.kv_r16 : nullptr; ek.ldc_bf16 = 768;
+    Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = tc ? nullptr : s.kv_r; ek.ldc = 768; ek.out_bf16 = tc ? s.kv_r16 : nullptr; ek.ldc_bf16 = 768;
     if (tc) { ek.vt_out = s.vt_r16; ek.vt_col0 = 384; }
     DVD_TRY(linear(c, s.r, s.r16, 384, w.xattn_in, 384, M, 768, ek));
   }

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmParams p) {
 
   // ---- epilogue
   const Epilogue& e = p.e;
-  float* __restrict__ Cb = e.out + zn * p.sCn + zh * p.sCh;
+  float* __restrict__ Cb = e.out ? e.out + zn * p.sCn + zh * p.sCh : nullptr;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int row = bm + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -150,11 +150,13 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmParams p) {
       for (int j = 0; j < 4; ++j) v[j] = (col + j < p.N) ? apply_epilogue(e, acc[i][jb * 4 + j] * p.alpha, row, col + j, p.N) : 0.f;
       int orow, ocol;
       epilogue_dest(e, row, col, orow, ocol);
-      float* o = Cb + (size_t)orow * e.ldc + ocol;
-      if (col + 3 < p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-        for (int j = 0; j < 4 && col + j < p.N; ++j) o[j] = v[j];
+      if (e.out) {
+        float* o = Cb + (size_t)orow * e.ldc + ocol;
+        if (col + 3 < p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          for (int j = 0; j < 4 && col + j < p.N; ++j) o[j] = v[j];
+        }
       }
       if (e.out_bf16) {
         __nv_bfloat16* ob = e.out_bf16 + (size_t)orow * e.ldc_bf16 + ocol;
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmParams p) {
 }
 
 int gemm_f32(const GemmParams& p, int amode, int bmode, int batch, cudaStream_t st) {
-  DVD_REQUIRE(p.A && p.B && p.e.out, "gemm_f32: null pointer");
+  DVD_REQUIRE(p.A && p.B && (p.e.out || p.e.out_bf16), "gemm_f32: null pointer");
   DVD_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && (p.K % 4) == 0, "gemm_f32: bad shape M=%d N=%d K=%d", p.M, p.N, p.K);
   DVD_REQUIRE((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0, "gemm_f32: operands must be 16B aligned");
   if (amode == A_DIRECT) DVD_REQUIRE(p.lda % 4 == 0, "gemm_f32: lda %% 4");

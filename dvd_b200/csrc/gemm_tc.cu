@@ -49,25 +49,48 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+// 4-D bf16 NHWC activation [N, H, W, C]; box = 64 channels x 128 pixels of one image row (implicit-GEMM conv A operand).
+// Out-of-bounds coordinates (x = -1 / W, y = -1 / H: the conv's zero padding) are zero-filled by TMA.
+int make_tmap_bf16_nhwc(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return DVD_E_NOTMA; }
+  DVD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && c % 64 == 0 && w % 128 == 0, "nhwc tensor map: need C %% 64 == 0 and W %% 128 == 0");
+  cuuint64_t gdim[4] = {c, w, h, n};
+  cuuint64_t gstr[3] = {c * 2, w * c * 2, h * w * c * 2};
+  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (nhwc) failed (%d)", (int)r); return DVD_E_NOTMA; }
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------- kernel
 constexpr int TBM = 128, TBK = 64;
 
 template <int BN>
 struct TcCfg {
-  static constexpr int STAGES = (BN == 128) ? 3 : 2;                    // 3 x 32 KB or 2 x 48 KB -> two CTAs per SM
+  static constexpr int STAGES = (BN == 64) ? 4 : ((BN == 128) ? 3 : 2);   // <= 96 KB of ring -> two CTAs per SM
   static constexpr int A_BYTES = TBM * TBK * 2, B_BYTES = BN * TBK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
+  static constexpr int CW = BN < 128 ? BN : 128;                          // columns per epilogue pass
+  static constexpr int STAGE_LD = CW + 4;                                 // fp32 staging row stride (16-byte aligned, conflict-free)
+  static constexpr int STAGING_BYTES = 4 * 32 * STAGE_LD * 4;             // 4 warps x 32 rows
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static_assert(STAGING_BYTES <= RING_BYTES, "epilogue staging must fit in the (drained) operand ring");
+  static constexpr int SMEM = RING_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
 };
 
-template <int BN>
+struct ConvGeom { int H, W, Cin; };      // CONV: A is an NHWC activation, K = 9 * Cin ordered [ky][kx][Cin]
+
+template <int BN, bool CONV>
 __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                 int M, int N, int K, Epilogue e) {
+                                                 int M, int N, int K, Epilogue e, ConvGeom cg) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -92,12 +115,23 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer
+      int cn = 0, cy = 0, cx = 0, cblocks = 1;
+      if (CONV) {
+        const int hw = cg.H * cg.W;
+        cn = m0 / hw; const int rem = m0 % hw; cy = rem / cg.W; cx = rem % cg.W;      // 128 consecutive pixels of one image row
+        cblocks = cg.Cin / 64;
+      }
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES, it = kb / STAGES;
         mbar_wait(&empty[s], (it & 1) ^ 1);
         uint8_t* a = smem + s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        tma_load_2d(a, &tmA, &full[s], kb * TBK, m0);
+        if (CONV) {
+          const int tap = kb / cblocks, cb = kb % cblocks;
+          tma_load_4d(a, &tmA, &full[s], cb * 64, cx + tap % 3 - 1, cy + tap / 3 - 1, cn);
+        } else {
+          tma_load_2d(a, &tmA, &full[s], kb * TBK, m0);
+        }
         tma_load_2d(a + Cfg::A_BYTES, &tmB, &full[s], kb * TBK, n0);
         if (BN == 256) tma_load_2d(a + Cfg::A_BYTES + 128 * TBK * 2, &tmB, &full[s], kb * TBK, n0 + 128);
       }
@@ -124,87 +158,133 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
     __syncwarp();
   }
 
-  // ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane
+  // ===== epilogue.  tmem_full => every MMA has retired, so every TMA write has been consumed: the operand ring is dead
+  // and is reused as an fp32 staging tile.  Phase 1 (thread = row, TMEM lane): TMEM -> registers -> staging (+ the
+  // transposed V^T store, which is naturally coalesced in this mapping).  Phase 2 (lane = 4 consecutive columns):
+  // staging -> fused epilogue -> fully coalesced 512-byte row segments in global memory.
   mbar_wait(tmem_full, 0);
   fence_after_sync();
-  const int row = m0 + warp * 32 + lane;
+  constexpr int CW = Cfg::CW, SLD = Cfg::STAGE_LD;
+  float* stage = reinterpret_cast<float*>(smem) + warp * 32 * SLD;
+  const int row_t = m0 + warp * 32 + lane;               // phase-1 row of this thread
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-    tmem_ld_wait();
-    const int col0 = n0 + c0;
-    if (row < M && col0 < N) {
-      float v[32];
+  for (int pass = 0; pass < BN / CW; ++pass) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < CW; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pass * CW + c0), r);
+      tmem_ld_wait();
+      float* srow = stage + lane * SLD + c0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = (col0 + j < N) ? apply_epilogue(e, __uint_as_float(r[j]), row, col0 + j, N) : 0.f;
-      int orow, ocol;
-      epilogue_dest(e, row, col0, orow, ocol);
-      const bool fullc = (col0 + 31 < N);
-      if (e.out) {
-        float* o = e.out + (size_t)orow * e.ldc + ocol;
-        if (fullc && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32 && col0 + j < N; ++j) o[j] = v[j];
-        }
-      }
-      if (e.out_bf16) {
-        __nv_bfloat16* o = e.out_bf16 + (size_t)orow * e.ldc_bf16 + ocol;
-        if (fullc && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 u;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(o + j) = u;
-          }
-        } else {
-          for (int j = 0; j < 32 && col0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
-        }
-      }
-      if (e.vt_out && col0 >= e.vt_col0) {
-        // V^T: for a fixed column the 32 lanes hold 32 consecutive tokens -> 64-byte contiguous stores
-        __nv_bfloat16* o = e.vt_out + ((size_t)(row >> 10) * (N - e.vt_col0) + (col0 - e.vt_col0)) * 1024 + (row & 1023);
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      const int col0 = n0 + pass * CW + c0;
+      if (e.vt_out && col0 >= e.vt_col0 && row_t < M) {
+        __nv_bfloat16* o = e.vt_out + ((size_t)(row_t >> 10) * (N - e.vt_col0) + (col0 - e.vt_col0)) * 1024 + (row_t & 1023);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) o[(size_t)j * 1024] = __float2bfloat16_rn(v[j]);
+          if (col0 + j < N) o[(size_t)j * 1024] = __float2bfloat16_rn(apply_epilogue(e, __uint_as_float(r[j]), row_t, col0 + j, N));
       }
     }
+    __syncwarp();
+    // ---- phase 2
+    const int col = n0 + pass * CW + 4 * lane;
+    if (4 * lane < CW && col < N) {
+      float4 cb = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f), ct = cb, cgate = cs;
+      if (e.bias) cb = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+      if (e.scale) { cs = __ldg(reinterpret_cast<const float4*>(e.scale + col)); ct = __ldg(reinterpret_cast<const float4*>(e.shift + col)); }
+      if (e.gate) cgate = __ldg(reinterpret_cast<const float4*>(e.gate + col));
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int row = m0 + warp * 32 + r;
+        if (row >= M) break;
+        const float4 a = *reinterpret_cast<const float4*>(stage + r * SLD + 4 * lane);
+        float v[4] = {a.x + cb.x, a.y + cb.y, a.z + cb.z, a.w + cb.w};
+        if (e.scale) { v[0] = v[0] * cs.x + ct.x; v[1] = v[1] * cs.y + ct.y; v[2] = v[2] * cs.z + ct.z; v[3] = v[3] * cs.w + ct.w; }
+        if (e.act == ACT_RELU) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+        else if (e.act == ACT_GELU) { v[0] = gelu_tanh(v[0]); v[1] = gelu_tanh(v[1]); v[2] = gelu_tanh(v[2]); v[3] = gelu_tanh(v[3]); }
+        else if (e.act == ACT_SIGMOID) { v[0] = sigmoidf_(v[0]); v[1] = sigmoidf_(v[1]); v[2] = sigmoidf_(v[2]); v[3] = sigmoidf_(v[3]); }
+        if (e.pos) {
+          const float4 p = __ldg(reinterpret_cast<const float4*>(e.pos + (size_t)(row % e.pos_rows) * N + col));
+          v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
+        }
+        if (e.gate) { v[0] *= cgate.x; v[1] *= cgate.y; v[2] *= cgate.z; v[3] *= cgate.w; }
+        if (e.resid) {
+          const int rr = e.resid_mod ? (row % e.resid_mod) : row;
+          const float4 q = *reinterpret_cast<const float4*>(e.resid + (size_t)rr * e.ldr + col);   // may alias e.out (in-place residual)
+          v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+        }
+        int orow, ocol;
+        epilogue_dest(e, row, col, orow, ocol);
+        if (e.out) *reinterpret_cast<float4*>(e.out + (size_t)orow * e.ldc + ocol) = make_float4(v[0], v[1], v[2], v[3]);
+        if (e.out_bf16) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+          uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(e.out_bf16 + (size_t)orow * e.ldc_bf16 + ocol) = u;
+        }
+      }
+    }
+    __syncwarp();
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
+template <int BN, bool CONV>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epilogue& e, ConvGeom cg, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DVD_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(N, BN), cdiv(M, TBM));
+  k_gemm_tc<BN, CONV><<<grid, 128, TcCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, e, cg);
+  DVD_LAUNCH_CHECK("k_gemm_tc");
+  return 0;
+}
+
+static int check_epilogue(const Epilogue& e, int N) {
+  DVD_REQUIRE(N % 4 == 0, "gemm_tc: N must be a multiple of 4");
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  DVD_REQUIRE(al(e.bias) && al(e.scale) && al(e.shift) && al(e.gate) && al(e.pos) && al(e.resid) && al(e.out) &&
+              (reinterpret_cast<uintptr_t>(e.out_bf16) & 7) == 0, "gemm_tc: epilogue pointers must be 16-byte aligned");
+  DVD_REQUIRE(e.ldc % 4 == 0 && e.ldr % 4 == 0 && e.ldc_bf16 % 4 == 0 && e.group_col_stride % 4 == 0, "gemm_tc: epilogue leading dims %% 4");
+  DVD_REQUIRE(!e.vt_out || (e.vt_col0 % 32 == 0), "gemm_tc: vt_col0 %% 32");
+  return 0;
+}
+
 int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e, cudaStream_t st) {
   DVD_REQUIRE(A && W && (e.out || e.out_bf16), "gemm_tc: null pointer");
   DVD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0, "gemm_tc: bad shape M=%d N=%d K=%d", M, N, K);
-  CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 128, 64);
-  if (rc) return rc;
+  int rc = check_epilogue(e, N); if (rc) return rc;
   // wide tiles only when they still fill the machine (>= ~1 wave of 2 CTAs/SM)
   const bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) >= 2 * kSMs);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DVD_CUDA(cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM));
-    DVD_CUDA(cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM));
-    attr_set = true;
-  }
-  if (wide) {
-    dim3 grid(cdiv(N, 256), cdiv(M, TBM));
-    k_gemm_tc<256><<<grid, 128, TcCfg<256>::SMEM, st>>>(tmA, tmB, M, N, K, e);
-  } else {
-    dim3 grid(cdiv(N, 128), cdiv(M, TBM));
-    k_gemm_tc<128><<<grid, 128, TcCfg<128>::SMEM, st>>>(tmA, tmB, M, N, K, e);
-  }
-  DVD_LAUNCH_CHECK("k_gemm_tc");
-  return 0;
+  const bool narrow = (N <= 64);
+  CUtensorMap tmA, tmB;
+  rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64); if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, narrow ? 64 : 128, 64); if (rc) return rc;
+  ConvGeom cg{0, 0, 0};
+  if (wide) return launch_tc<256, false>(tmA, tmB, M, N, K, e, cg, st);
+  if (narrow) return launch_tc<64, false>(tmA, tmB, M, N, K, e, cg, st);
+  return launch_tc<128, false>(tmA, tmB, M, N, K, e, cg, st);
+}
+
+// 3x3 / pad 1 / stride 1 convolution as an implicit GEMM: in NHWC bf16 [B,H,W,Cin], Wt [Cout, 9*Cin] ([ky][kx][Cin]),
+// out NHWC [B,H,W,Cout] through the Epilogue (bias + ReLU, bf16 and/or fp32).
+int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* Wt, int B, int H, int Wd, int Cin, int Cout, const Epilogue& e,
+                    cudaStream_t st) {
+  DVD_REQUIRE(in && Wt && (e.out || e.out_bf16), "conv3x3_tc: null pointer");
+  DVD_REQUIRE(Cin % 64 == 0 && Wd % 128 == 0 && (Cout == 64 || Cout % 128 == 0), "conv3x3_tc: unsupported shape Cin=%d W=%d Cout=%d", Cin, Wd, Cout);
+  const int M = B * H * Wd, K = 9 * Cin;
+  int rc = check_epilogue(e, Cout); if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  rc = make_tmap_bf16_nhwc(&tmA, in, (uint64_t)B, (uint64_t)H, (uint64_t)Wd, (uint64_t)Cin); if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)Cout, (uint64_t)K, (uint64_t)K, Cout == 64 ? 64 : 128, 64); if (rc) return rc;
+  ConvGeom cg{H, Wd, Cin};
+  if (Cout == 64) return launch_tc<64, true>(tmA, tmB, M, Cout, K, e, cg, st);
+  if (Cout % 256 == 0 && (long long)(M / 128) * (Cout / 256) >= 2 * kSMs) return launch_tc<256, true>(tmA, tmB, M, Cout, K, e, cg, st);
+  return launch_tc<128, true>(tmA, tmB, M, Cout, K, e, cg, st);
 }
 
 }  // namespace dvd

@@ -9,6 +9,11 @@ namespace dvd {
 int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e,
                  cudaStream_t st);
 
+// 3x3 / pad 1 conv as implicit GEMM on tcgen05 (TMA boxes over the NHWC activation, zero padding by OOB fill):
+// in [B,H,W,Cin] bf16, Wt [Cout, 9*Cin] bf16 ordered [ky][kx][Cin]; output through the Epilogue as [B*H*W, Cout].
+int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* Wt, int B, int H, int Wd, int Cin, int Cout, const Epilogue& e,
+                    cudaStream_t st);
+
 // softmax(scale * Q K^T) V per (sample, head); bf16 in/out, fp32 softmax statistics and accumulation.
 // q/k/o row-major with leading dims ld*, head h at columns [h*d, (h+1)*d); vt is V TRANSPOSED: [nsamp/kv_div, heads*d, T]
 // (written by the QKV GEMM epilogue, Epilogue::vt_out).  k/vt of sample n come from sample n / kv_div.

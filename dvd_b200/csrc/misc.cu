@@ -96,6 +96,44 @@ int maxpool2_nhwc(const float* in, float* out, int B, int H, int W, int C, cudaS
   return 0;
 }
 
+// 2x2 max pool on bf16 NHWC (8 channels = 16 bytes per thread); writes bf16 and/or fp32
+__global__ void k_maxpool2_bf16(const uint4* __restrict__ in, uint4* __restrict__ out16, float* __restrict__ out32, int B, int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * Ho * Wo * C8;
+  if (i >= total) return;
+  int c = i % C8; size_t r = i / C8;
+  int xo = r % Wo; r /= Wo;
+  int yo = r % Ho; int b = r / Ho;
+  const uint4* p = in + (((size_t)b * H + 2 * yo) * W + 2 * xo) * C8 + c;
+  uint4 q[4] = {__ldg(p), __ldg(p + C8), __ldg(p + (size_t)W * C8), __ldg(p + (size_t)W * C8 + C8)};
+  uint4 m;
+  uint32_t* mw = reinterpret_cast<uint32_t*>(&m);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&reinterpret_cast<uint32_t*>(&q[0])[k]);
+#pragma unroll
+    for (int t = 1; t < 4; ++t) a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&reinterpret_cast<uint32_t*>(&q[t])[k]));
+    mw[k] = *reinterpret_cast<uint32_t*>(&a);
+  }
+  if (out16) out16[i] = m;
+  if (out32) {
+    float* o = out32 + i * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&mw[k]);
+      o[2 * k] = __low2float(a); o[2 * k + 1] = __high2float(a);
+    }
+  }
+}
+int maxpool2_nhwc_bf16(const __nv_bfloat16* in, __nv_bfloat16* out16, float* out32, int B, int H, int W, int C, cudaStream_t st) {
+  DVD_REQUIRE(in && (out16 || out32) && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bf16: bad args");
+  size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  k_maxpool2_bf16<<<cdiv(total, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out16, out32, B, H, W, C / 8);
+  DVD_LAUNCH_CHECK("k_maxpool2_bf16");
+  return 0;
+}
+
 __global__ void k_nhwc_to_nchw(const float* __restrict__ in, float* __restrict__ out, int HW, int C) {
   __shared__ float tile[32][33];
   int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -285,24 +323,33 @@ int softmax_rows(float* S, long long rows, int n, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------ small dense layers
 constexpr int GEMV_MAXR = 8;
+// block = 8 warps = 8 output features; the (activated) input rows are staged once per block in shared memory, each warp
+// streams its weight row with 128-bit loads (4 independent loads in flight per lane).
 __global__ void __launch_bounds__(256) k_gemv(const float* __restrict__ in, int ldin, const float* __restrict__ W,
                                               const float* __restrict__ b, float* __restrict__ out, int ldo, int rows, int N,
                                               int K, int silu_in, int in_mod, int act) {
+  extern __shared__ float xs[];                      // [rows][K]
+  for (int i = threadIdx.x; i < rows * K; i += 256) {
+    const int r = i / K, k = i - r * K;
+    float x = __ldg(in + (size_t)r * ldin + (in_mod > 0 ? (k % in_mod) : k));
+    xs[i] = silu_in ? silu(x) : x;
+  }
+  __syncthreads();
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= N) return;
   float acc[GEMV_MAXR];
 #pragma unroll
   for (int r = 0; r < GEMV_MAXR; ++r) acc[r] = 0.f;
-  const float* wr = W + (size_t)j * K;
-  for (int k = lane; k < K; k += 32) {
-    float wv = __ldg(wr + k);
-    int ki = in_mod > 0 ? (k % in_mod) : k;
+  const float4* wr = reinterpret_cast<const float4*>(W + (size_t)j * K);
+  const int K4 = K >> 2;
+#pragma unroll 4
+  for (int k = lane; k < K4; k += 32) {
+    const float4 wv = __ldg(wr + k);
 #pragma unroll
     for (int r = 0; r < GEMV_MAXR; ++r) {
       if (r < rows) {
-        float x = __ldg(in + (size_t)r * ldin + ki);
-        if (silu_in) x = silu(x);
-        acc[r] = fmaf(wv, x, acc[r]);
+        const float4 x = *reinterpret_cast<const float4*>(xs + r * K + 4 * k);
+        acc[r] += (wv.x * x.x + wv.y * x.y) + (wv.z * x.z + wv.w * x.w);
       }
     }
   }
@@ -322,10 +369,12 @@ __global__ void __launch_bounds__(256) k_gemv(const float* __restrict__ in, int 
 }
 int gemv(const float* in, int ldin, const float* W, const float* b, float* out, int ldo, int rows, int N, int K, int silu_in,
          int in_mod, int act, cudaStream_t st) {
-  DVD_REQUIRE(in && W && out && N > 0 && K > 0, "gemv: bad args");
+  DVD_REQUIRE(in && W && out && N > 0 && K > 0 && K % 4 == 0 && K <= 1536, "gemv: bad args (K=%d)", K);
+  DVD_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemv: W must be 16-byte aligned");
   for (int r0 = 0; r0 < rows; r0 += GEMV_MAXR) {
     int nr = rows - r0 < GEMV_MAXR ? rows - r0 : GEMV_MAXR;
-    k_gemv<<<cdiv(N, 8), 256, 0, st>>>(in + (size_t)r0 * ldin, ldin, W, b, out + (size_t)r0 * ldo, ldo, nr, N, K, silu_in, in_mod, act);
+    k_gemv<<<cdiv(N, 8), 256, (size_t)nr * K * sizeof(float), st>>>(in + (size_t)r0 * ldin, ldin, W, b, out + (size_t)r0 * ldo, ldo, nr, N, K,
+                                                                    silu_in, in_mod, act);
     DVD_LAUNCH_CHECK("k_gemv");
   }
   return 0;

@@ -14,6 +14,7 @@ int layernorm(const float* in, int ldin, float* out, int ldo, __nv_bfloat16* out
 int pack_y4(const float* y512, const float* mask, float* out, int B, cudaStream_t st);
 // 2x2 max pool on NHWC fp32
 int maxpool2_nhwc(const float* in, float* out, int B, int H, int W, int C, cudaStream_t st);
+int maxpool2_nhwc_bf16(const __nv_bfloat16* in, __nv_bfloat16* out16, float* out32, int B, int H, int W, int C, cudaStream_t st);
 // fp32 NHWC -> NCHW (feat for the drop-in model() return value) and back
 int nhwc_to_nchw(const float* in, float* out, int B, int H, int W, int C, cudaStream_t st);
 

@@ -111,36 +111,128 @@ __device__ __forceinline__ uint8_t to_u8_trunc(float v) {   // numpy .astype(uin
 constexpr int TILE_W = 128, TILE_H = 8;   // 32 x 8 threads, 4 px per thread
 
 // IN: 0 = fp32 NCHW, 1 = uint8 HWC.  OUT likewise.
+//
+// Per-CTA prologue: the column-only and row-only parts of the coordinate chain (upsample index / weight of the coarse
+// map, upsampled base ramp with its two fp32 divisions) are computed ONCE per tile column / tile row into shared
+// memory (128 + 8 entries), so the per-pixel path is: 8 coarse-map loads, 2 bilinear blends, affine, tap weights and
+// 4*C gathers.  Tiles whose four taps are all inside the photo for every pixel of the warp (the common case) take an
+// unpredicated path so that the 4*C*4 gathers of a thread are issued back to back.
 template <int IN_U8, int OUT_U8, int C>
 __global__ void __launch_bounds__(256) k_unwarp(const void* __restrict__ photo_, const float* __restrict__ map,
                                                 void* __restrict__ out_, UnwarpGeom g) {
+  __shared__ float s_bx[TILE_W], s_lx[TILE_W], s_by[TILE_H], s_ly[TILE_H];
+  __shared__ int s_x0[TILE_W], s_y0[TILE_H];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < TILE_W) {
+    const int j = min(blockIdx.x * TILE_W + tid, g.W - 1);
+    int x0, xp; float l0, l1;
+    up_coeff(g.sx, j, g.mw, x0, xp, l0, l1);
+    s_x0[tid] = x0 | (xp << 16); s_lx[tid] = l1; s_bx[tid] = base_ramp(g.bx, j);
+  } else if (tid < TILE_W + TILE_H) {
+    const int r = tid - TILE_W;
+    const int i = min(blockIdx.y * TILE_H + r, g.H - 1);
+    int y0, yp; float l0, l1;
+    up_coeff(g.sy, i, g.mh, y0, yp, l0, l1);
+    s_y0[r] = y0 | (yp << 16); s_ly[r] = l1; s_by[r] = base_ramp(g.by, i);
+  }
+  __syncthreads();
   const int b = blockIdx.z;
   const int i = blockIdx.y * TILE_H + threadIdx.y;
   const int j0 = (blockIdx.x * (TILE_W / 4) + threadIdx.x) * 4;
   if (i >= g.H || j0 >= g.W) return;
-  const size_t plane = (size_t)g.H * g.W;
-  const float* mapb = map + (size_t)b * 2 * g.mh * g.mw;
-  float res[C][4];
+  const int W = g.W, H = g.H;
+  const int plane = H * W;                                      // < 2^31 elements per image (checked on the host)
+  const float* __restrict__ mapb = map + (size_t)b * 2 * g.mh * g.mw;
+  const int y0m = s_y0[threadIdx.y] & 0xffff, dy = (s_y0[threadIdx.y] >> 16) * g.mw;
+  const float ly1 = s_ly[threadIdx.y], ly0 = 1.0f - ly1, byv = s_by[threadIdx.y];
+  const float* __restrict__ mrow = mapb + y0m * g.mw;
+  const int mplane = g.mh * g.mw;
+
+  int off[4];                    // element offset of the NW tap: y0 * W + x0
+  float wnw[4], wne[4], wsw[4], wse[4];
+  bool inside = true;
+  int vmask[4];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    int j = j0 + p;
-    if (j < g.W) {
-      float gx, gy;
-      sample_coords(g, mapb, i, j, gx, gy);
-      Taps t = make_taps(gx, gy, g.H, g.W);
+    const int cj = threadIdx.x * 4 + p;                         // column inside the tile
+    const int x0m = s_x0[cj] & 0xffff, xp = s_x0[cj] >> 16;
+    const float lx1 = s_lx[cj], lx0 = 1.0f - lx1;
+    const float* m0 = mrow + x0m;
+    const float* m1 = m0 + mplane;
+    const float sx = ly0 * (lx0 * __ldg(m0) + lx1 * __ldg(m0 + xp)) + ly1 * (lx0 * __ldg(m0 + dy) + lx1 * __ldg(m0 + dy + xp));
+    const float sy = ly0 * (lx0 * __ldg(m1) + lx1 * __ldg(m1 + xp)) + ly1 * (lx0 * __ldg(m1 + dy) + lx1 * __ldg(m1 + dy + xp));
+    const float gx = ((sx + s_bx[cj]) * 2.0f - 1.0f) * g.affine;
+    const float gy = ((sy + byv) * 2.0f - 1.0f) * g.affine;
+    const Taps t = make_taps(gx, gy, H, W);
+    off[p] = t.y0 * W + t.x0;
+    wnw[p] = t.nw; wne[p] = t.ne; wsw[p] = t.sw; wse[p] = t.se;
+    vmask[p] = (int)t.vx0 | ((int)t.vx1 << 1) | ((int)t.vy0 << 2) | ((int)t.vy1 << 3);
+    inside = inside && (vmask[p] == 15 || j0 + p >= W);
+    if (j0 + p >= W) { vmask[p] = 0; off[p] = 0; }
+  }
+  float res[C][4];
+  if (__all_sync(0xffffffffu, inside) && j0 + 3 < W) {
+    // ---- fast path: every tap of every pixel of this warp is inside the photo
+    if (IN_U8) {
+      const uint8_t* __restrict__ ph = (const uint8_t*)photo_ + (size_t)b * plane * C;
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        if (IN_U8) res[c][p] = gather((const uint8_t*)photo_ + (size_t)b * plane * C + c, t, g.W, C);
-        else       res[c][p] = gather((const float*)photo_ + ((size_t)b * C + c) * plane, t, g.W, 1);
+      for (int p = 0; p < 4; ++p) {
+        const uint8_t* q = ph + (size_t)off[p] * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float v = (float)__ldg(q + c) * wnw[p];
+          v += (float)__ldg(q + C + c) * wne[p];
+          v += (float)__ldg(q + (size_t)W * C + c) * wsw[p];
+          v += (float)__ldg(q + (size_t)(W + 1) * C + c) * wse[p];
+          res[c][p] = v;
+        }
       }
     } else {
+      const float* __restrict__ ph = (const float*)photo_ + (size_t)b * C * plane;
 #pragma unroll
-      for (int c = 0; c < C; ++c) res[c][p] = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float* pc = ph + (size_t)c * plane;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float* q = pc + off[p];
+          float v = __ldg(q) * wnw[p];
+          v += __ldg(q + 1) * wne[p];
+          v += __ldg(q + W) * wsw[p];
+          v += __ldg(q + W + 1) * wse[p];
+          res[c][p] = v;
+        }
+      }
+    }
+  } else {
+    // ---- border path: per-tap validity (zeros padding), same accumulation order
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      Taps t;
+      t.nw = wnw[p]; t.ne = wne[p]; t.sw = wsw[p]; t.se = wse[p];
+      t.vx0 = vmask[p] & 1; t.vx1 = vmask[p] & 2; t.vy0 = vmask[p] & 4; t.vy1 = vmask[p] & 8;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float v = 0.f;
+        if (IN_U8) {
+          const uint8_t* q = (const uint8_t*)photo_ + ((size_t)b * plane + off[p]) * C + c;
+          if (t.vy0 & t.vx0) v += (float)__ldg(q) * t.nw;
+          if (t.vy0 & t.vx1) v += (float)__ldg(q + C) * t.ne;
+          if (t.vy1 & t.vx0) v += (float)__ldg(q + (long long)W * C) * t.sw;
+          if (t.vy1 & t.vx1) v += (float)__ldg(q + (long long)(W + 1) * C) * t.se;
+        } else {
+          const float* q = (const float*)photo_ + ((size_t)b * C + c) * plane + off[p];
+          if (t.vy0 & t.vx0) v += __ldg(q) * t.nw;
+          if (t.vy0 & t.vx1) v += __ldg(q + 1) * t.ne;
+          if (t.vy1 & t.vx0) v += __ldg(q + W) * t.sw;
+          if (t.vy1 & t.vx1) v += __ldg(q + W + 1) * t.se;
+        }
+        res[c][p] = v;
+      }
     }
   }
-  const bool full = (j0 + 3 < g.W);
+  const bool full = (j0 + 3 < W);
   if (OUT_U8) {
-    uint8_t* o = (uint8_t*)out_ + ((size_t)b * plane + (size_t)i * g.W + j0) * C;
+    uint8_t* o = (uint8_t*)out_ + ((size_t)b * plane + (size_t)i * W + j0) * C;
     uint8_t bytes[4 * C];
 #pragma unroll
     for (int p = 0; p < 4; ++p)
@@ -153,17 +245,17 @@ __global__ void __launch_bounds__(256) k_unwarp(const void* __restrict__ photo_,
         reinterpret_cast<uint32_t*>(o)[w] = v;
       }
     } else {
-      int n = min(4, g.W - j0) * C;
+      int n = min(4, W - j0) * C;
       for (int q = 0; q < n; ++q) o[q] = bytes[q];
     }
   } else {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      float* o = (float*)out_ + ((size_t)b * C + c) * plane + (size_t)i * g.W + j0;
+      float* o = (float*)out_ + ((size_t)b * C + c) * plane + (size_t)i * W + j0;
       if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
         __stcs(reinterpret_cast<float4*>(o), make_float4(res[c][0], res[c][1], res[c][2], res[c][3]));  // streaming store
       } else {
-        for (int p = 0; p < 4 && j0 + p < g.W; ++p) o[p] = res[c][p];
+        for (int p = 0; p < 4 && j0 + p < W; ++p) o[p] = res[c][p];
       }
     }
   }
@@ -199,6 +291,7 @@ static int launch_unwarp(const void* photo, const float* map, void* out, int B, 
   if (B == 0 || H == 0 || W == 0) return 0;          // empty batch / empty photo: nothing to do
   DVD_REQUIRE(photo && map && out, "unwarp: null pointer");
   DVD_REQUIRE(B <= 65535 && cdiv(H, TILE_H) <= 65535, "unwarp: grid too large");
+  DVD_REQUIRE((long long)H * W * C < (1ll << 31) && mh < 65536 && mw < 65536, "unwarp: image too large for 32-bit tap offsets");
   UnwarpGeom g = make_geom(H, W, mh, mw, affine);
   dim3 grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B), block(32, 8);
   switch (C) {

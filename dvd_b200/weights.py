@@ -92,7 +92,7 @@ class PackedWeights:
         T.pos = self._vec(sd["noised_obs_pos_embed"].reshape(1024, 384))
         for i, p in enumerate(PYR_KEYS):
             w = sd[p + ".weight"].float()                                  # [Cout, Cin, 3, 3] -> [Cout, ky, kx, Cin]
-            T.pyr[i] = self._mat(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), bf16=False)
+            T.pyr[i] = self._mat(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), bf16=(i > 0))
             T.pyr_b[i] = self._vec(sd[p + ".bias"])
         for i, e in enumerate(EMB_KEYS):
             w = sd[f"{e}_embedder.proj.weight"].float()
