@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
   fence_after_sync();
   constexpr int CW = Cfg::CW, SLD = Cfg::STAGE_LD;
   float* stage = reinterpret_cast<float*>(smem) + warp * 32 * SLD;
-  const int row_t = m0 + warp * 32 + lane;               // phase-1 row of this thread
+  const int row_t = m0 + warp * 32 + lane;               // phase-1 row of this thread (M % 128 == 0 is checked on the host)
 #pragma unroll 1
   for (int pass = 0; pass < BN / CW; ++pass) {
 #pragma unroll 1
@@ -179,11 +179,17 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
       for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
       const int col0 = n0 + pass * CW + c0;
-      if (e.vt_out && col0 >= e.vt_col0 && row_t < M) {
+      if (e.vt_out && col0 >= e.vt_col0 && col0 + 31 < N) {
+        // V^T (bias-only epilogue, checked on the host): the bias of the 32 columns is warp-uniform -> 8 vector loads up front
+        float bv[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+        }
         __nv_bfloat16* o = e.vt_out + ((size_t)(row_t >> 10) * (N - e.vt_col0) + (col0 - e.vt_col0)) * 1024 + (row_t & 1023);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) o[(size_t)j * 1024] = __float2bfloat16_rn(apply_epilogue(e, __uint_as_float(r[j]), row_t, col0 + j, N));
+        for (int j = 0; j < 32; ++j) o[(size_t)j * 1024] = __float2bfloat16_rn(__uint_as_float(r[j]) + bv[j]);
       }
     }
     __syncwarp();
@@ -194,33 +200,48 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
       if (e.bias) cb = __ldg(reinterpret_cast<const float4*>(e.bias + col));
       if (e.scale) { cs = __ldg(reinterpret_cast<const float4*>(e.scale + col)); ct = __ldg(reinterpret_cast<const float4*>(e.shift + col)); }
       if (e.gate) cgate = __ldg(reinterpret_cast<const float4*>(e.gate + col));
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int row = m0 + warp * 32 + r;
-        if (row >= M) break;
-        const float4 a = *reinterpret_cast<const float4*>(stage + r * SLD + 4 * lane);
-        float v[4] = {a.x + cb.x, a.y + cb.y, a.z + cb.z, a.w + cb.w};
-        if (e.scale) { v[0] = v[0] * cs.x + ct.x; v[1] = v[1] * cs.y + ct.y; v[2] = v[2] * cs.z + ct.z; v[3] = v[3] * cs.w + ct.w; }
-        if (e.act == ACT_RELU) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-        else if (e.act == ACT_GELU) { v[0] = gelu_tanh(v[0]); v[1] = gelu_tanh(v[1]); v[2] = gelu_tanh(v[2]); v[3] = gelu_tanh(v[3]); }
-        else if (e.act == ACT_SIGMOID) { v[0] = sigmoidf_(v[0]); v[1] = sigmoidf_(v[1]); v[2] = sigmoidf_(v[2]); v[3] = sigmoidf_(v[3]); }
-        if (e.pos) {
-          const float4 p = __ldg(reinterpret_cast<const float4*>(e.pos + (size_t)(row % e.pos_rows) * N + col));
-          v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
-        }
-        if (e.gate) { v[0] *= cgate.x; v[1] *= cgate.y; v[2] *= cgate.z; v[3] *= cgate.w; }
+      const bool has_scale = e.scale != nullptr, has_gate = e.gate != nullptr;
+      const int act = e.act;
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float4 a[8], q[8], p[8];
+        // batch the loads of 8 rows (staging, residual, pos-embed) before any dependent math or store
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(stage + (r0 + i) * SLD + 4 * lane);
         if (e.resid) {
-          const int rr = e.resid_mod ? (row % e.resid_mod) : row;
-          const float4 q = *reinterpret_cast<const float4*>(e.resid + (size_t)rr * e.ldr + col);   // may alias e.out (in-place residual)
-          v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = m0 + warp * 32 + r0 + i;
+            const int rr = e.resid_mod ? (row % e.resid_mod) : row;
+            q[i] = *reinterpret_cast<const float4*>(e.resid + (size_t)rr * e.ldr + col);      // may alias e.out (in-place residual)
+          }
         }
-        int orow, ocol;
-        epilogue_dest(e, row, col, orow, ocol);
-        if (e.out) *reinterpret_cast<float4*>(e.out + (size_t)orow * e.ldc + ocol) = make_float4(v[0], v[1], v[2], v[3]);
-        if (e.out_bf16) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-          uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-          *reinterpret_cast<uint2*>(e.out_bf16 + (size_t)orow * e.ldc_bf16 + ocol) = u;
+        if (e.pos) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = m0 + warp * 32 + r0 + i;
+            p[i] = __ldg(reinterpret_cast<const float4*>(e.pos + (size_t)(row % e.pos_rows) * N + col));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = m0 + warp * 32 + r0 + i;
+          float v[4] = {a[i].x + cb.x, a[i].y + cb.y, a[i].z + cb.z, a[i].w + cb.w};
+          if (has_scale) { v[0] = v[0] * cs.x + ct.x; v[1] = v[1] * cs.y + ct.y; v[2] = v[2] * cs.z + ct.z; v[3] = v[3] * cs.w + ct.w; }
+          if (act == ACT_RELU) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+          else if (act == ACT_GELU) { v[0] = gelu_tanh(v[0]); v[1] = gelu_tanh(v[1]); v[2] = gelu_tanh(v[2]); v[3] = gelu_tanh(v[3]); }
+          else if (act == ACT_SIGMOID) { v[0] = sigmoidf_(v[0]); v[1] = sigmoidf_(v[1]); v[2] = sigmoidf_(v[2]); v[3] = sigmoidf_(v[3]); }
+          if (e.pos) { v[0] += p[i].x; v[1] += p[i].y; v[2] += p[i].z; v[3] += p[i].w; }
+          if (has_gate) { v[0] *= cgate.x; v[1] *= cgate.y; v[2] *= cgate.z; v[3] *= cgate.w; }
+          if (e.resid) { v[0] += q[i].x; v[1] += q[i].y; v[2] += q[i].z; v[3] += q[i].w; }
+          int orow, ocol;
+          epilogue_dest(e, row, col, orow, ocol);
+          if (e.out) *reinterpret_cast<float4*>(e.out + (size_t)orow * e.ldc + ocol) = make_float4(v[0], v[1], v[2], v[3]);
+          if (e.out_bf16) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(e.out_bf16 + (size_t)orow * e.ldc_bf16 + ocol) = u;
+          }
         }
       }
     }
@@ -250,13 +271,14 @@ static int check_epilogue(const Epilogue& e, int N) {
   DVD_REQUIRE(al(e.bias) && al(e.scale) && al(e.shift) && al(e.gate) && al(e.pos) && al(e.resid) && al(e.out) &&
               (reinterpret_cast<uintptr_t>(e.out_bf16) & 7) == 0, "gemm_tc: epilogue pointers must be 16-byte aligned");
   DVD_REQUIRE(e.ldc % 4 == 0 && e.ldr % 4 == 0 && e.ldc_bf16 % 4 == 0 && e.group_col_stride % 4 == 0, "gemm_tc: epilogue leading dims %% 4");
-  DVD_REQUIRE(!e.vt_out || (e.vt_col0 % 32 == 0), "gemm_tc: vt_col0 %% 32");
+  DVD_REQUIRE(!e.vt_out || (e.vt_col0 % 32 == 0 && N % 32 == 0 && !e.scale && !e.act && !e.pos && !e.gate && !e.resid),
+              "gemm_tc: the V^T output supports a bias-only epilogue with vt_col0 %% 32 == 0");
   return 0;
 }
 
 int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e, cudaStream_t st) {
   DVD_REQUIRE(A && W && (e.out || e.out_bf16), "gemm_tc: null pointer");
-  DVD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0, "gemm_tc: bad shape M=%d N=%d K=%d", M, N, K);
+  DVD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && M % 128 == 0, "gemm_tc: bad shape M=%d N=%d K=%d (M must be a multiple of 128)", M, N, K);
   int rc = check_epilogue(e, N); if (rc) return rc;
   // wide tiles only when they still fill the machine (>= ~1 wave of 2 CTAs/SM)
   const bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) >= 2 * kSMs);
