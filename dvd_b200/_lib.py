@@ -64,6 +64,7 @@ SIGNATURES = {
     "dvd_workspace_tensor": (_vp, [_vp, _i, _i, _i, C.c_char_p, C.POINTER(C.c_longlong)]),
     "dvd_test_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "dvd_test_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
+    "dvd_gemm_bf16": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "dvd_profile_begin": (_i, []),
     "dvd_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "dvd_launch_count": (C.c_longlong, [_i]),

@@ -101,3 +101,10 @@ extern "C" int dvd_test_attention(const float* q, const float* k, const float* v
   rc = attention_tc_bf16(q16, ld, k16, ld, vt16, o16, ld, batch, heads, T, d, scale, 1, st); if (rc) return rc;
   return bf16_to_f32(o16, o, n, st);
 }
+
+// Plain bf16 GEMM entry point (tuning / micro-benchmarks): out = A W^T + bias, bf16 output (and optional fp32 output).
+extern "C" int dvd_gemm_bf16(const void* A16, int lda, const void* W16, int ldw, const float* bias, void* out16, float* out32, int M, int N,
+                             int K, void* stream) {
+  Epilogue e; e.bias = bias; e.out_bf16 = (__nv_bfloat16*)out16; e.ldc_bf16 = N; e.out = out32; e.ldc = N;
+  return gemm_tc_bf16((const __nv_bfloat16*)A16, lda, (const __nv_bfloat16*)W16, ldw, M, N, K, e, (cudaStream_t)stream);
+}

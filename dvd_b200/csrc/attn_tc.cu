@@ -43,9 +43,11 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
   uint8_t* sP = sKV + ST * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // ST
-  uint64_t* kv_empty = kv_full + ST;       // ST
-  uint64_t* s_full = kv_empty + ST;        // 2
+  uint64_t* k_full = bars + 1;             // ST   K and V^T have separate rings: a K stage is released as soon as QK^T(t)
+  uint64_t* k_empty = k_full + ST;         // ST   has read it (one tile earlier than the V^T stage, released after PV(t)),
+  uint64_t* v_full = k_empty + ST;         // ST   which gives the K loads an extra tile of prefetch distance
+  uint64_t* v_empty = v_full + ST;         // ST
+  uint64_t* s_full = v_empty + ST;         // 2
   uint64_t* s_empty = s_full + 2;          // 2
   uint64_t* p_full = s_empty + 2;          // 1
   uint64_t* pv_done = p_full + 1;          // 1
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmVt);
     mbar_init(q_full, 1);
-    for (int s = 0; s < ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < ST; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 128); }
     mbar_init(p_full, 128);
     mbar_init(pv_done, 1);
@@ -79,12 +81,14 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
       for (int j = 0; j < D / 64; ++j) tma_load_2d(sQ + j * (AQ * 128), &tmQ, q_full, h * D + 64 * j, n * T + q0);
       for (int t = 0; t < nt; ++t) {
         const int s = t % ST, u = t / ST;
-        mbar_wait(&kv_empty[s], (u & 1) ^ 1);
         uint8_t* k = sKV + s * Cfg::STAGE_BYTES;
-        mbar_expect_tx(&kv_full[s], Cfg::STAGE_BYTES);
+        mbar_wait(&k_empty[s], (u & 1) ^ 1);
+        mbar_expect_tx(&k_full[s], Cfg::K_BYTES);
 #pragma unroll
-        for (int j = 0; j < D / 64; ++j) tma_load_2d(k + j * (AKV * 128), &tmK, &kv_full[s], h * D + 64 * j, nkv * T + t * AKV);
-        tma_load_2d(k + Cfg::K_BYTES, &tmVt, &kv_full[s], t * AKV, (nkv * heads + h) * D);     // box: 64 keys x D rows of V^T
+        for (int j = 0; j < D / 64; ++j) tma_load_2d(k + j * (AKV * 128), &tmK, &k_full[s], h * D + 64 * j, nkv * T + t * AKV);
+        mbar_wait(&v_empty[s], (u & 1) ^ 1);
+        mbar_expect_tx(&v_full[s], Cfg::V_BYTES);
+        tma_load_2d(k + Cfg::K_BYTES, &tmVt, &v_full[s], t * AKV, (nkv * heads + h) * D);      // box: 64 keys x D rows of V^T
       }
     }
     __syncwarp();
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       auto issue_qk = [&](int t) {
         const int s = t % ST, b = t & 1;
-        mbar_wait(&kv_full[s], (t / ST) & 1);
+        mbar_wait(&k_full[s], (t / ST) & 1);
         mbar_wait(&s_empty[b], ((t >> 1) & 1) ^ 1);
         fence_after_sync();
         const uint32_t k_addr = smem_u32(sKV + s * Cfg::STAGE_BYTES);
@@ -105,11 +109,13 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
           mma_f16_ss(tmem_base + b * AKV, make_desc_k_sw128(q_addr + (k >> 2) * (AQ * 128) + (k & 3) * 32),
                      make_desc_k_sw128(k_addr + (k >> 2) * (AKV * 128) + (k & 3) * 32), idesc_qk, k ? 1u : 0u);
         mma_commit(&s_full[b]);
+        mma_commit(&k_empty[s]);                                  // K stage free as soon as QK^T(t) has read it
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int t = 0; t < nt; ++t) {
         if (t + 1 < nt) issue_qk(t + 1);                          // S(t+1) overlaps softmax(t)
+        mbar_wait(&v_full[t % ST], (t / ST) & 1);
         mbar_wait(p_full, t & 1);
         fence_after_sync();
         const uint32_t v_addr = smem_u32(sKV + (t % ST) * Cfg::STAGE_BYTES + Cfg::K_BYTES);
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
         for (int k = 0; k < AKV / 16; ++k)
           mma_f16_ss(tmem_base + Cfg::O_COL, make_desc_k_sw128(p_addr + k * 32), make_desc_k_sw128(v_addr + k * 32), idesc_pv,
                      (t | k) ? 1u : 0u);
-        mma_commit(&kv_empty[t % ST]);                            // K and V^T of this stage are free
+        mma_commit(&v_empty[t % ST]);                             // V^T stage free
         mma_commit(pv_done);                                      // P buffer free, O(t) complete
       }
     }

@@ -61,6 +61,13 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   float inner = k0 * (x + k1 * x * x * x);
   return 0.5f * x * (1.0f + tanhf(inner));
 }
+// hardware tanh (MUFU.TANH, ~2^-11 relative error): used by the bf16 tensor-path epilogue only
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x), t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  return 0.5f * x * (1.0f + t);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 

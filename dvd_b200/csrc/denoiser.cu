@@ -23,7 +23,7 @@ struct Workspace {
   float *a_r, *xe, *r, *qn, *q, *kv_r, *xo, *xs, *hmod, *qkv, *h1, *X, *pe, *hd, *qkv_d, *att_d, *f1, *f2, *S;
   float *flow[2], *xbuf[2], *pred;
   // bf16 operand staging (DVD_PREC_BF16)
-  __nv_bfloat16 *a_stat16, *ctx16[3], *a_r16, *r16, *qn16, *xo16, *hmod16, *h116, *hd16, *att_d16, *f216;
+  __nv_bfloat16 *a_stat16, *ctx16[3], *a_r16, *r16, *qn16, *xo16, *hmod16, *h116, *hd16, *att_d16, *f116, *f216;
   __nv_bfloat16 *q16, *kv_static16[3], *kv_r16, *qkv16, *qkv_d16;       // attention operands (Q, K row-major)
   __nv_bfloat16 *vt_static16[3], *vt_r16, *vt_qkv16, *vt_d16;            // V^T [sample, C_v, 1024] written by the GEMM epilogues
   size_t s_floats;
@@ -67,7 +67,7 @@ static Workspace carve(void* base, int docs, int n_hyp, int precision) {
     for (int i = 0; i < 3; ++i) w.ctx16[i] = H(Md * 384);
     w.a_r16 = H(M * 1032);
     w.r16 = H(M * 384); w.qn16 = H(M * 384); w.xo16 = H(4 * M * 384); w.hmod16 = H(4 * M * 384);
-    w.h116 = H(4 * M * 1536); w.hd16 = H(M * 1536); w.att_d16 = H(M * 1536); w.f216 = H(M * 2048);
+    w.h116 = H(4 * M * 1536); w.hd16 = H(M * 1536); w.att_d16 = H(M * 1536); w.f116 = H(M * 2048); w.f216 = H(M * 2048);
     w.q16 = H(M * 384); w.kv_r16 = H(M * 768); w.qkv16 = H(4 * M * 1152); w.qkv_d16 = H(M * 4608);
     for (int i = 0; i < 3; ++i) w.kv_static16[i] = H(Md * 768);
     for (int i = 0; i < 3; ++i) w.vt_static16[i] = H(Md * 384);
@@ -328,10 +328,12 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     }
     DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, tc ? s.hd16 : nullptr, 1536, M, 1536, 1e-5f, L.n2_w, L.n2_b, nullptr, nullptr, st));
     {
-      Epilogue e; e.scale = L.bn1_scale; e.shift = L.bn1_shift; e.act = ACT_RELU; e.out = s.f1; e.ldc = 2048;
+      Epilogue e; e.scale = L.bn1_scale; e.shift = L.bn1_shift; e.act = ACT_RELU; e.out = tc ? nullptr : s.f1; e.ldc = 2048;
+      e.out_bf16 = tc ? s.f116 : nullptr; e.ldc_bf16 = 2048;
       DVD_TRY(linear(c, s.hd, s.hd16, 1536, L.conv1, 0, M, 2048, e));
     }
-    DVD_TRY(dwconv3x3_bn_relu(s.f1, L.dw_w, L.bn2_scale, L.bn2_shift, tc ? nullptr : s.f2, tc ? s.f216 : nullptr, N, 2048, st));
+    if (tc) DVD_TRY(dwconv3x3_bn_relu_bf16(s.f116, L.dw_w, L.bn2_scale, L.bn2_shift, s.f216, N, 2048, st));
+    else DVD_TRY(dwconv3x3_bn_relu(s.f1, L.dw_w, L.bn2_scale, L.bn2_shift, s.f2, nullptr, N, 2048, st));
     {
       Epilogue e; e.scale = L.bn3_scale; e.shift = L.bn3_shift; e.act = ACT_RELU; e.resid = s.X; e.ldr = 1536; e.out = s.X; e.ldc = 1536;
       DVD_TRY(linear(c, s.f2, s.f216, 2048, L.conv2, 0, M, 1536, e));

@@ -10,6 +10,7 @@
 //   * K tails (K = 1032 for the r-embedder) are zero-filled by TMA; M/N tails are masked in the epilogue.
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace dvd {
 
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
           float v[4] = {a[i].x + cb.x, a[i].y + cb.y, a[i].z + cb.z, a[i].w + cb.w};
           if (has_scale) { v[0] = v[0] * cs.x + ct.x; v[1] = v[1] * cs.y + ct.y; v[2] = v[2] * cs.z + ct.z; v[3] = v[3] * cs.w + ct.w; }
           if (act == ACT_RELU) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-          else if (act == ACT_GELU) { v[0] = gelu_tanh(v[0]); v[1] = gelu_tanh(v[1]); v[2] = gelu_tanh(v[2]); v[3] = gelu_tanh(v[3]); }
+          else if (act == ACT_GELU) { v[0] = gelu_tanh_fast(v[0]); v[1] = gelu_tanh_fast(v[1]); v[2] = gelu_tanh_fast(v[2]); v[3] = gelu_tanh_fast(v[3]); }
           else if (act == ACT_SIGMOID) { v[0] = sigmoidf_(v[0]); v[1] = sigmoidf_(v[1]); v[2] = sigmoidf_(v[2]); v[3] = sigmoidf_(v[3]); }
           if (e.pos) { v[0] += p[i].x; v[1] += p[i].y; v[2] += p[i].z; v[3] += p[i].w; }
           if (has_gate) { v[0] *= cgate.x; v[1] *= cgate.y; v[2] *= cgate.z; v[3] *= cgate.w; }
@@ -276,10 +277,29 @@ static int check_epilogue(const Epilogue& e, int N) {
   return 0;
 }
 
+int gemm_tc2_dispatch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e,
+                      int conv_b, int conv_h, int conv_w, int conv_cin, cudaStream_t st);
+static bool use_v1() {
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("DVD_GEMM_V1"); v = (s && s[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+static bool force_v2() {
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("DVD_GEMM_V2"); v = (s && s[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e, cudaStream_t st) {
   DVD_REQUIRE(A && W && (e.out || e.out_bf16), "gemm_tc: null pointer");
   DVD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && M % 128 == 0, "gemm_tc: bad shape M=%d N=%d K=%d (M must be a multiple of 128)", M, N, K);
   int rc = check_epilogue(e, N); if (rc) return rc;
+  // Measured on B200 (profiles/r1_gemm_microbench.txt): the persistent 128x256 kernel wins once there are >= 4 waves of wide
+  // tiles (1.1 PFLOP/s at M = 16384); the small M = 2048 problems of a single document are latency-bound and run faster as two
+  // co-resident 128x128 CTAs per SM.
+  if (!use_v1() && (force_v2() || (N % 256 == 0 && (long long)(M / 128) * (N / 256) >= 4 * kSMs)))
+    return gemm_tc2_dispatch(A, lda, W, ldw, M, N, K, e, 0, 0, 0, 0, st);
   // wide tiles only when they still fill the machine (>= ~1 wave of 2 CTAs/SM)
   const bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) >= 2 * kSMs);
   const bool narrow = (N <= 64);
@@ -300,6 +320,7 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* Wt, int B, int
   DVD_REQUIRE(Cin % 64 == 0 && Wd % 128 == 0 && (Cout == 64 || Cout % 128 == 0), "conv3x3_tc: unsupported shape Cin=%d W=%d Cout=%d", Cin, Wd, Cout);
   const int M = B * H * Wd, K = 9 * Cin;
   int rc = check_epilogue(e, Cout); if (rc) return rc;
+  if (!use_v1() && force_v2()) return gemm_tc2_dispatch(in, 0, Wt, K, M, Cout, K, e, B, H, Wd, Cin, st);
   CUtensorMap tmA, tmB;
   rc = make_tmap_bf16_nhwc(&tmA, in, (uint64_t)B, (uint64_t)H, (uint64_t)Wd, (uint64_t)Cin); if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)Cout, (uint64_t)K, (uint64_t)K, Cout == 64 ? 64 : 128, 64); if (rc) return rc;

@@ -474,6 +474,57 @@ __global__ void __launch_bounds__(256) k_dwconv(const float4* __restrict__ in, c
   float r0 = fmaxf(acc.x * s.x + t.x, 0.f), r1 = fmaxf(acc.y * s.y + t.y, 0.f), r2 = fmaxf(acc.z * s.z + t.z, 0.f), r3 = fmaxf(acc.w * s.w + t.w, 0.f);
   store4(out, out16, i * 4, r0, r1, r2, r3);
 }
+// bf16 in / bf16 out variant for the tensor path: 8 channels (16 bytes) per thread, fp32 accumulation
+__global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ sc,
+                                                     const float* __restrict__ sh, uint4* __restrict__ out, int C8, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = i % C8; const size_t row = i / C8;
+  const int tok = row % 1024; const size_t n = row / 1024;
+  const int y = tok / 32, x = tok % 32;
+  const int C = C8 * 8;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= 32) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= 32) continue;
+      const uint4 v = __ldg(in + (n * 1024 + yy * 32 + xx) * C8 + c);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)(ky * 3 + kx) * C + c * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)(ky * 3 + kx) * C + c * 8 + 4));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+      acc[0] = fmaf(__low2float(h[0]), w0.x, acc[0]); acc[1] = fmaf(__high2float(h[0]), w0.y, acc[1]);
+      acc[2] = fmaf(__low2float(h[1]), w0.z, acc[2]); acc[3] = fmaf(__high2float(h[1]), w0.w, acc[3]);
+      acc[4] = fmaf(__low2float(h[2]), w1.x, acc[4]); acc[5] = fmaf(__high2float(h[2]), w1.y, acc[5]);
+      acc[6] = fmaf(__low2float(h[3]), w1.z, acc[6]); acc[7] = fmaf(__high2float(h[3]), w1.w, acc[7]);
+    }
+  }
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c * 8)), s1 = __ldg(reinterpret_cast<const float4*>(sc + c * 8 + 4));
+  const float4 t0 = __ldg(reinterpret_cast<const float4*>(sh + c * 8)), t1 = __ldg(reinterpret_cast<const float4*>(sh + c * 8 + 4));
+  const float r[8] = {fmaxf(acc[0] * s0.x + t0.x, 0.f), fmaxf(acc[1] * s0.y + t0.y, 0.f), fmaxf(acc[2] * s0.z + t0.z, 0.f),
+                      fmaxf(acc[3] * s0.w + t0.w, 0.f), fmaxf(acc[4] * s1.x + t1.x, 0.f), fmaxf(acc[5] * s1.y + t1.y, 0.f),
+                      fmaxf(acc[6] * s1.z + t1.z, 0.f), fmaxf(acc[7] * s1.w + t1.w, 0.f)};
+  uint4 o;
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(r[0], r[1]), p1 = __floats2bfloat162_rn(r[2], r[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(r[4], r[5]), p3 = __floats2bfloat162_rn(r[6], r[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+  o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+  out[i] = o;
+}
+int dwconv3x3_bn_relu_bf16(const __nv_bfloat16* in, const float* w9c, const float* scale, const float* shift, __nv_bfloat16* out, int N, int C,
+                           cudaStream_t st) {
+  DVD_REQUIRE(in && w9c && scale && shift && out && C % 8 == 0, "dwconv_bf16: bad args");
+  size_t total = (size_t)N * 1024 * (C / 8);
+  k_dwconv_bf16<<<cdiv(total, 256), 256, 0, st>>>((const uint4*)in, w9c, scale, shift, (uint4*)out, C / 8, total);
+  DVD_LAUNCH_CHECK("k_dwconv_bf16");
+  return 0;
+}
+
 int dwconv3x3_bn_relu(const float* in, const float* w9c, const float* scale, const float* shift, float* out, __nv_bfloat16* out16,
                       int N, int C, cudaStream_t st) {
   DVD_REQUIRE(in && w9c && scale && shift && (out || out16) && C % 4 == 0, "dwconv: bad args");

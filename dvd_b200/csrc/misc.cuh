@@ -57,6 +57,9 @@ int posenc_add(float* X, const float* hs, const float* ws, const float* hpe, con
 int dwconv3x3_bn_relu(const float* in, const float* w9c, const float* scale, const float* shift, float* out,
                       __nv_bfloat16* out16, int N, int C, cudaStream_t st);
 
+int dwconv3x3_bn_relu_bf16(const __nv_bfloat16* in, const float* w9c, const float* scale, const float* shift, __nv_bfloat16* out, int N,
+                           int C, cudaStream_t st);
+
 // decoder.layer_norm (affine, 1e-5) -> norm_final (1e-6) -> modulate -> Linear 1536->8 -> unpatchify
 // -> += init_flow -> pred ; x_prev = a*pred + b*x_t          (CA:457, CM:329-336,553-566,645-646, GD:470-489)
 int final_layer(const float* X, const float* ln_w, const float* ln_b, const float* shift, const float* scale,

@@ -175,6 +175,9 @@ DVD_API int dvd_test_gemm(const float* A, const float* W, const float* bias, flo
 DVD_API int dvd_test_attention(const float* q, const float* k, const float* v, float* o, int batch, int heads,
                        int T, int d, float scale, int precision, void* scratch, size_t scratch_bytes,
                        void* stream);
+/* Plain tensor-core GEMM (tuning / micro-benchmarks): out = A[M,K] W[N,K]^T + bias; bf16 operands, bf16 and/or fp32 output. */
+DVD_API int dvd_gemm_bf16(const void* A16, int lda, const void* W16, int ldw, const float* bias, void* out16, float* out32,
+                          int M, int N, int K, void* stream);
 /* Kernel-class profiler: between begin/end every dense contraction launched by this thread is bracketed by CUDA
  * events.  end() synchronises and returns, for the classes {0: GEMM, 1: attention, 2: pyramid conv}, the summed
  * device time (ms), algorithmic FLOPs and launch counts. */
