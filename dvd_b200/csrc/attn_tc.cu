@@ -1,14 +1,17 @@
 // Fused attention on tcgen05: O = softmax(scale * Q K^T) V for one (sample, head, 128-query tile) per CTA.
 //
 //   S = Q K^T  : UMMA M=128 (queries) x N=64 (keys) x K=d, accumulator in TMEM (two S buffers)
-//   softmax    : 4 warps, one query row per thread (TMEM lane == row): tcgen05.ld S, online max / exp2 / sum in fp32,
-//                P (bf16) written to shared memory in the 128-byte-swizzled K-major layout the next MMA reads
-//   O += P V   : UMMA M=128 x N=d x K=64, accumulator stays resident in TMEM for the whole KV sweep; it is rescaled
-//                in place (tcgen05.ld / tcgen05.st) only when a row maximum grows by more than 2^8 (lazy rescale)
+//   softmax    : 8 warps; TMEM lane == query row, and each row is shared by TWO threads (one per 32-key half, the two warps that
+//                may access the same TMEM lane quarter): tcgen05.ld S, row max exchanged through smem + a 64-thread named barrier,
+//                exp2 / partial sums in fp32, P (bf16) written to shared memory in the 128-byte-swizzled K-major layout
+//   O += P V   : UMMA M=128 x N=d x K=64, accumulator resident in TMEM for the whole KV sweep; rescaled in place
+//                (tcgen05.ld / tcgen05.st, each half-warp pair owns half of the d columns) only when a row maximum grows by more
+//                than 2^8 (lazy rescale; exact after the final division by the row sum)
 //   epilogue   : O / rowsum -> bf16 -> global
 // All three operands are K-major: Q [T, d], K [T, d] and V^T [d, T] (the QKV GEMM epilogue writes V transposed), so the
-// same SWIZZLE_128B TMA boxes + UMMA descriptors as the GEMM are used.  Warp roles: 0 = TMA producer, 1 = MMA issuer,
-// 2..5 = softmax/correction/epilogue.  d in {64, 256}; T a multiple of 128.
+// same SWIZZLE_128B TMA boxes + UMMA descriptors as the GEMM are used.  K and V^T have separate mbarrier rings (a K stage is
+// released right after QK^T(t)).  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = softmax / correction / epilogue.
+// d in {64, 256}; T a multiple of 128.
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
 
@@ -17,6 +20,7 @@ using namespace tc;
 
 constexpr int AQ = 128;      // queries per CTA
 constexpr int AKV = 64;      // keys per pipeline step
+constexpr int ATHREADS = 320;
 
 template <int D>
 struct AttnCfg {
@@ -25,15 +29,26 @@ struct AttnCfg {
   static constexpr int K_BYTES = AKV * D * 2, V_BYTES = D * AKV * 2;
   static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
   static constexpr int P_BYTES = AQ * AKV * 2;
-  static constexpr int SMEM = Q_BYTES + STAGES * STAGE_BYTES + P_BYTES + 1024 + 256;
+  static constexpr int X_BYTES = 2 * 2 * AQ * 4;                // row-max / row-sum exchange: [parity][half][row]
+  static constexpr int SMEM = Q_BYTES + STAGES * STAGE_BYTES + P_BYTES + X_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;      // 2 x 64 (S) + D (O), rounded to a power of two
   static constexpr int O_COL = 2 * AKV;
+  static_assert(SMEM <= 232448, "shared memory budget");
 };
 
+__device__ __forceinline__ void pair_barrier(int quarter) {      // the two warps that own one TMEM lane quarter
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int D>
-__global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                                                 const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ O, int ldo, int T,
-                                                 int heads, int kv_div, float scale_log2) {
+__global__ void __launch_bounds__(ATHREADS) k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                      const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ O, int ldo, int T,
+                                                      int heads, int kv_div, float scale_log2) {
   using Cfg = AttnCfg<D>;
   constexpr int ST = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -41,11 +56,12 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Cfg::Q_BYTES;
   uint8_t* sP = sKV + ST * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  float* sX = reinterpret_cast<float*>(sP + Cfg::P_BYTES);       // [2][2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES + Cfg::X_BYTES);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* k_full = bars + 1;             // ST   K and V^T have separate rings: a K stage is released as soon as QK^T(t)
-  uint64_t* k_empty = k_full + ST;         // ST   has read it (one tile earlier than the V^T stage, released after PV(t)),
-  uint64_t* v_full = k_empty + ST;         // ST   which gives the K loads an extra tile of prefetch distance
+  uint64_t* k_full = bars + 1;             // ST
+  uint64_t* k_empty = k_full + ST;         // ST
+  uint64_t* v_full = k_empty + ST;         // ST
   uint64_t* v_empty = v_full + ST;         // ST
   uint64_t* s_full = v_empty + ST;         // 2
   uint64_t* s_empty = s_full + 2;          // 2
@@ -61,8 +77,8 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmVt);
     mbar_init(q_full, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 128); }
-    mbar_init(p_full, 128);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 256); }
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -75,7 +91,7 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer: Q once, then the K / V^T ring
+      // ===== TMA producer: Q once, then the K and V^T rings
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int j = 0; j < D / 64; ++j) tma_load_2d(sQ + j * (AQ * 128), &tmQ, q_full, h * D + 64 * j, n * T + q0);
@@ -129,48 +145,49 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
     }
     __syncwarp();
   } else {
-    // ===== softmax / correction / epilogue: thread <-> query row (TMEM lane)
+    // ===== softmax / correction / epilogue: row = TMEM lane; two threads (halves) per row
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                             // warps 2..5 -> keys [0,32), warps 6..9 -> keys [32,64) of each tile
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;                                 // m is identical in both halves; l is this half's partial sum
     for (int t = 0; t < nt; ++t) {
       const int b = t & 1;
       mbar_wait(&s_full[b], (t >> 1) & 1);
       fence_after_sync();
-      uint32_t s0[32], s1[32];
-      tmem_ld_32x32(lane_base + b * AKV, s0);
-      tmem_ld_32x32(lane_base + b * AKV + 32, s1);
+      uint32_t s0[32];
+      tmem_ld_32x32(lane_base + b * AKV + half * 32, s0);
       tmem_ld_wait();
       fence_before_sync();
-      mbar_arrive(&s_empty[b]);                                   // S(b) is in registers: the next QK^T may overwrite it
+      mbar_arrive(&s_empty[b]);                                   // this half of S(b) is in registers
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[j]), __uint_as_float(s1[j])));
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(s0[j]));
+      float* xch = sX + (t & 1) * 256;                            // double-buffered by tile parity (see the race note in DESIGN.md)
+      xch[half * 128 + row] = mx;
+      pair_barrier(quarter);
+      mx = fmaxf(mx, xch[(half ^ 1) * 128 + row]);
       const float m_new = fmaxf(m, mx * scale_log2);
-      // lazy rescale: keep the stale maximum while exp2 stays below 2^8 (exact after the final division by l)
+      // lazy rescale: keep the stale maximum while exp2 stays below 2^8
       const bool grow = (m_new - m) > 8.0f;                       // also true for t == 0 (m = -inf)
-      const float alpha = (grow && t > 0) ? exp2f(m - m_new) : 1.0f;
+      const float alpha = (grow && t > 0) ? ex2(m - m_new) : 1.0f;
       if (grow) m = m_new;
       float sum = 0.f;
-      uint32_t pk[32];                                            // 64 bf16 probabilities, packed in pairs
+      uint32_t pk[16];                                            // 32 bf16 probabilities
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        float a0 = exp2f(fmaf(__uint_as_float(s0[j]), scale_log2, -m)), a1 = exp2f(fmaf(__uint_as_float(s0[j + 1]), scale_log2, -m));
-        float b0 = exp2f(fmaf(__uint_as_float(s1[j]), scale_log2, -m)), b1 = exp2f(fmaf(__uint_as_float(s1[j + 1]), scale_log2, -m));
-        __nv_bfloat162 pa = __floats2bfloat162_rn(a0, a1), pb = __floats2bfloat162_rn(b0, b1);
-        // the row sum uses the same bf16-rounded values the tensor core multiplies with
-        sum += (__low2float(pa) + __high2float(pa)) + (__low2float(pb) + __high2float(pb));
-        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&pa);
-        pk[16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&pb);
+        const float a0 = ex2(fmaf(__uint_as_float(s0[j]), scale_log2, -m)), a1 = ex2(fmaf(__uint_as_float(s0[j + 1]), scale_log2, -m));
+        const __nv_bfloat162 pa = __floats2bfloat162_rn(a0, a1);
+        sum += __low2float(pa) + __high2float(pa);                // the sum uses the rounded values the tensor core multiplies with
+        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&pa);
       }
       l = l * alpha + sum;
       if (t > 0) {
         mbar_wait(pv_done, (t - 1) & 1);                          // PV(t-1) finished: P buffer reusable, O readable
         fence_after_sync();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {             // warp-uniform: tcgen05.ld/st are warp-collective
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {             // identical decision in both warps of the pair
 #pragma unroll 1
-          for (int c = 0; c < D; c += 32) {
+          for (int c = half * (D / 2); c < (half + 1) * (D / 2); c += 32) {
             uint32_t o[32];
             tmem_ld_32x32(lane_base + Cfg::O_COL + c, o);
             tmem_ld_wait();
@@ -181,24 +198,27 @@ __global__ void __launch_bounds__(192) k_attn_tc(const __grid_constant__ CUtenso
           tmem_st_wait();
         }
       }
-      // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
+      // P half-row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
       uint8_t* prow = sP + row * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = v;
+      for (int c = 0; c < 4; ++c) {
+        const uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (row & 7)) << 4)) = v;
       }
       fence_proxy_async();                                        // generic-proxy writes -> visible to the UMMA (async proxy)
       fence_before_sync();
       mbar_arrive(p_full);
     }
-    // ---- epilogue
+    // ---- epilogue: total row sum = both halves' partial sums; each half stores D/2 columns
+    float* xch = sX + (nt & 1) * 256;
+    xch[half * 128 + row] = l;
+    pair_barrier(quarter);
+    const float inv = 1.0f / (l + xch[(half ^ 1) * 128 + row]);
     mbar_wait(pv_done, (nt - 1) & 1);
     fence_after_sync();
-    const float inv = 1.0f / l;
     __nv_bfloat16* orow = O + (size_t)(n * T + q0 + row) * ldo + h * D;
 #pragma unroll 1
-    for (int c = 0; c < D; c += 32) {
+    for (int c = half * (D / 2); c < (half + 1) * (D / 2); c += 32) {
       uint32_t o[32];
       tmem_ld_32x32(lane_base + Cfg::O_COL + c, o);
       tmem_ld_wait();
@@ -253,8 +273,8 @@ int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, i
   }
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(T / AQ, heads, nsamp);
-  if (d == 64) k_attn_tc<64><<<grid, 192, AttnCfg<64>::SMEM, st>>>(tmQ, tmK, tmVt, o, ldo, T, heads, kv_div, scale_log2);
-  else         k_attn_tc<256><<<grid, 192, AttnCfg<256>::SMEM, st>>>(tmQ, tmK, tmVt, o, ldo, T, heads, kv_div, scale_log2);
+  if (d == 64) k_attn_tc<64><<<grid, ATHREADS, AttnCfg<64>::SMEM, st>>>(tmQ, tmK, tmVt, o, ldo, T, heads, kv_div, scale_log2);
+  else         k_attn_tc<256><<<grid, ATHREADS, AttnCfg<256>::SMEM, st>>>(tmQ, tmK, tmVt, o, ldo, T, heads, kv_div, scale_log2);
   DVD_LAUNCH_CHECK("k_attn_tc");
   return 0;
 }
