@@ -261,6 +261,165 @@ __global__ void __launch_bounds__(256) k_unwarp(const void* __restrict__ photo_,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast variant (the one the hot path uses).  Differences from k_unwarp above:
+//   * the coarse map is blended VERTICALLY once per tile row in the CTA prologue (v[r][k] = ly0*m[y0][k] + ly1*m[y1][k] for the
+//     few map columns the tile touches), so a pixel needs 2 shared-memory reads + 1 blend per channel instead of 4 global loads
+//     + 3 blends (horizontal-then-vertical vs vertical-then-horizontal blending differ by <= 1 ulp of the map, ~1e-4 px);
+//   * tap set-up without clamps: floor via cvt.rmi, one unsigned compare per axis decides "all four taps inside";
+//   * taps of the four pixels of a thread are issued back to back on the (common) all-inside path.
+// Falls back to k_unwarp when the tile would touch more than UW_WIN map columns (tiny photos / huge maps).
+constexpr int UW_WIN = 16;
+
+template <int IN_U8, int OUT_U8, int C>
+__global__ void __launch_bounds__(256) k_unwarp_fast(const void* __restrict__ photo_, const float* __restrict__ map,
+                                                     void* __restrict__ out_, UnwarpGeom g) {
+  __shared__ float s_bx[TILE_W], s_lx[TILE_W], s_by[TILE_H], s_ly[TILE_H];
+  __shared__ int s_kx[TILE_W], s_y0[TILE_H];
+  __shared__ float s_v[2][TILE_H][UW_WIN];
+  __shared__ int s_wx0;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int b = blockIdx.z;
+  const float* __restrict__ mapb = map + (size_t)b * 2 * g.mh * g.mw;
+  const int jt0 = blockIdx.x * TILE_W;
+  // window of map columns touched by this tile: x0(first column) .. x0(last column) + 1
+  int wx0;
+  {
+    int xp; float l0, l1;
+    up_coeff(g.sx, min(jt0, g.W - 1), g.mw, wx0, xp, l0, l1);
+  }
+  if (tid < TILE_W) {
+    const int j = min(jt0 + tid, g.W - 1);
+    int x0, xp; float l0, l1;
+    up_coeff(g.sx, j, g.mw, x0, xp, l0, l1);
+    s_kx[tid] = (x0 - wx0) | (xp << 16); s_lx[tid] = l1; s_bx[tid] = base_ramp(g.bx, j);
+  } else if (tid < TILE_W + TILE_H) {
+    const int r = tid - TILE_W;
+    const int i = min(blockIdx.y * TILE_H + r, g.H - 1);
+    int y0, yp; float l0, l1;
+    up_coeff(g.sy, i, g.mh, y0, yp, l0, l1);
+    s_y0[r] = y0 | (yp << 16); s_ly[r] = l1; s_by[r] = base_ramp(g.by, i);
+  }
+  __syncthreads();
+  if (tid < 2 * TILE_H * UW_WIN) {             // vertical blend of the map window: [channel][tile row][window column]
+    const int k = tid % UW_WIN, r = (tid / UW_WIN) % TILE_H, ch = tid / (UW_WIN * TILE_H);
+    const int col = min(wx0 + k, g.mw - 1);
+    const int y0 = s_y0[r] & 0xffff, yp = s_y0[r] >> 16;
+    const float l1 = s_ly[r], l0 = 1.0f - l1;
+    const float* m = mapb + (size_t)ch * g.mh * g.mw + (size_t)y0 * g.mw + col;
+    s_v[ch][r][k] = l0 * __ldg(m) + l1 * __ldg(m + yp * g.mw);
+  }
+  __syncthreads();
+  const int i = blockIdx.y * TILE_H + threadIdx.y;
+  const int j0 = jt0 + threadIdx.x;                       // pixel p of this thread is column j0 + 32*p: a warp-level
+  if (i >= g.H) return;                                   // load/store then covers 32 CONSECUTIVE pixels (one 128-byte line);
+                                                          // whole warps exit (a warp is one tile row): *_sync masks stay valid
+  const int W = g.W, H = g.H;
+  const int plane = H * W;
+  const float byv = s_by[threadIdx.y];
+  const float fw = (float)(W - 1), fh = (float)(H - 1);
+  int off[4];
+  float wnw[4], wne[4], wsw[4], wse[4];
+  int x0s[4], y0s[4];
+  bool inside = true;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int cj = threadIdx.x + 32 * p;
+    const int k = s_kx[cj] & 0xffff, xp = s_kx[cj] >> 16;
+    const float lx1 = s_lx[cj], lx0 = 1.0f - lx1;
+    const float sx = lx0 * s_v[0][threadIdx.y][k] + lx1 * s_v[0][threadIdx.y][k + xp];
+    const float sy = lx0 * s_v[1][threadIdx.y][k] + lx1 * s_v[1][threadIdx.y][k + xp];
+    const float gx = ((sx + s_bx[cj]) * 2.0f - 1.0f) * g.affine;
+    const float gy = ((sy + byv) * 2.0f - 1.0f) * g.affine;
+    const float ix = ((gx + 1.f) / 2.f) * fw, iy = ((gy + 1.f) / 2.f) * fh;      // grid_sampler_unnormalize, align_corners=True
+    const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy);
+    const float fx = (float)x0, fy = (float)y0;
+    const float ax = ix - fx, ay = iy - fy, bx = (fx + 1.f) - ix, byw = (fy + 1.f) - iy;
+    wnw[p] = bx * byw; wne[p] = ax * byw; wsw[p] = bx * ay; wse[p] = ax * ay;
+    x0s[p] = x0; y0s[p] = y0;
+    off[p] = y0 * W + x0;
+    inside = inside && (((unsigned)x0 < (unsigned)(W - 1)) & ((unsigned)y0 < (unsigned)(H - 1)));
+  }
+  float res[C][4];
+  if (__all_sync(0xffffffffu, inside) && jt0 + TILE_W <= W) {
+    // all-inside path: 32-bit unsigned element indices off ONE uniform base pointer (cheap address arithmetic)
+    if (IN_U8) {
+      const uint8_t* __restrict__ ph = (const uint8_t*)photo_ + (size_t)b * plane * C;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const uint32_t i0 = (uint32_t)off[p] * C, i1 = i0 + (uint32_t)W * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float v = (float)__ldg(ph + (i0 + c)) * wnw[p];
+          v += (float)__ldg(ph + (i0 + C + c)) * wne[p];
+          v += (float)__ldg(ph + (i1 + c)) * wsw[p];
+          v += (float)__ldg(ph + (i1 + C + c)) * wse[p];
+          res[c][p] = v;
+        }
+      }
+    } else {
+      const float* __restrict__ ph = (const float*)photo_ + (size_t)b * C * plane;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const uint32_t i0 = (uint32_t)(c * plane) + (uint32_t)off[p], i1 = i0 + (uint32_t)W;
+          float v = __ldg(ph + i0) * wnw[p];
+          v += __ldg(ph + (i0 + 1u)) * wne[p];
+          v += __ldg(ph + i1) * wsw[p];
+          v += __ldg(ph + (i1 + 1u)) * wse[p];
+          res[c][p] = v;
+        }
+      }
+    }
+  } else {
+    // border path: per-tap validity (zeros padding); coordinates may be wild, so validity is tested before any address is formed
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int x0 = x0s[p], y0 = y0s[p];
+      const bool px_ok = (j0 + 32 * p < W);
+      const bool vx0 = px_ok && x0 >= 0 && x0 < W, vx1 = px_ok && x0 >= -1 && x0 < W - 1;
+      const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 >= -1 && y0 < H - 1;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float v = 0.f;
+        if (IN_U8) {
+          const uint8_t* base = (const uint8_t*)photo_ + (size_t)b * plane * C + c;
+          if (vy0 && vx0) v += (float)__ldg(base + ((long long)y0 * W + x0) * C) * wnw[p];
+          if (vy0 && vx1) v += (float)__ldg(base + ((long long)y0 * W + x0 + 1) * C) * wne[p];
+          if (vy1 && vx0) v += (float)__ldg(base + ((long long)(y0 + 1) * W + x0) * C) * wsw[p];
+          if (vy1 && vx1) v += (float)__ldg(base + ((long long)(y0 + 1) * W + x0 + 1) * C) * wse[p];
+        } else {
+          const float* base = (const float*)photo_ + ((size_t)b * C + c) * plane;
+          if (vy0 && vx0) v += __ldg(base + (long long)y0 * W + x0) * wnw[p];
+          if (vy0 && vx1) v += __ldg(base + (long long)y0 * W + x0 + 1) * wne[p];
+          if (vy1 && vx0) v += __ldg(base + (long long)(y0 + 1) * W + x0) * wsw[p];
+          if (vy1 && vx1) v += __ldg(base + (long long)(y0 + 1) * W + x0 + 1) * wse[p];
+        }
+        res[c][p] = v;
+      }
+    }
+  }
+  if (OUT_U8) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (j0 + 32 * p < W) {
+        uint8_t* o = (uint8_t*)out_ + ((size_t)b * plane + (size_t)i * W + j0 + 32 * p) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[c] = to_u8_trunc(res[c][p]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float* o = (float*)out_ + ((size_t)b * C + c) * plane + (size_t)i * W + j0;
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (j0 + 32 * p < W) __stcs(o + 32 * p, res[c][p]);
+    }
+  }
+}
+
 __global__ void k_fullres_grid(const float* __restrict__ map, float* __restrict__ grid, UnwarpGeom g) {
   int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
   if (j >= g.W) return;
@@ -294,11 +453,22 @@ static int launch_unwarp(const void* photo, const float* map, void* out, int B, 
   DVD_REQUIRE((long long)H * W * C < (1ll << 31) && mh < 65536 && mw < 65536, "unwarp: image too large for 32-bit tap offsets");
   UnwarpGeom g = make_geom(H, W, mh, mw, affine);
   dim3 grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B), block(32, 8);
-  switch (C) {
-    case 1: k_unwarp<IN_U8, OUT_U8, 1><<<grid, block, 0, st>>>(photo, map, out, g); break;
-    case 2: k_unwarp<IN_U8, OUT_U8, 2><<<grid, block, 0, st>>>(photo, map, out, g); break;
-    case 3: k_unwarp<IN_U8, OUT_U8, 3><<<grid, block, 0, st>>>(photo, map, out, g); break;
-    default: k_unwarp<IN_U8, OUT_U8, 4><<<grid, block, 0, st>>>(photo, map, out, g); break;
+  // map columns a 128-pixel tile can touch: floor(127 * sx) + 2 (+1 for the clamped last column)
+  const bool fast = (int)(127.0f * g.sx) + 3 <= UW_WIN && W > 1 && H > 1;
+  if (fast) {
+    switch (C) {
+      case 1: k_unwarp_fast<IN_U8, OUT_U8, 1><<<grid, block, 0, st>>>(photo, map, out, g); break;
+      case 2: k_unwarp_fast<IN_U8, OUT_U8, 2><<<grid, block, 0, st>>>(photo, map, out, g); break;
+      case 3: k_unwarp_fast<IN_U8, OUT_U8, 3><<<grid, block, 0, st>>>(photo, map, out, g); break;
+      default: k_unwarp_fast<IN_U8, OUT_U8, 4><<<grid, block, 0, st>>>(photo, map, out, g); break;
+    }
+  } else {
+    switch (C) {
+      case 1: k_unwarp<IN_U8, OUT_U8, 1><<<grid, block, 0, st>>>(photo, map, out, g); break;
+      case 2: k_unwarp<IN_U8, OUT_U8, 2><<<grid, block, 0, st>>>(photo, map, out, g); break;
+      case 3: k_unwarp<IN_U8, OUT_U8, 3><<<grid, block, 0, st>>>(photo, map, out, g); break;
+      default: k_unwarp<IN_U8, OUT_U8, 4><<<grid, block, 0, st>>>(photo, map, out, g); break;
+    }
   }
   DVD_LAUNCH_CHECK("k_unwarp");
   return 0;
