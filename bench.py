@@ -61,7 +61,7 @@ class ClockSampler:
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -232,6 +232,7 @@ def run_ours(a):
         pipe.run_host(host_sets[i % n_var])
 
     sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.05)
     ms_dev, wall_dev, launches = timed(step_dev, a.steps, a.warmup)
     ms_e2e, wall_e2e, _ = timed(step_e2e, a.steps, a.warmup)
     clocks = sampler.stop() if sampler else None

@@ -285,6 +285,13 @@ static bool use_v1() {
   return v == 1;
 }
 
+int gemm_tc3_dispatch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e, int bn,
+                      cudaStream_t st);
+static int v3_mode() {      // DVD_GEMM_V3: 0 = off, 1 = pair kernel wherever the shape allows, 2 = heuristic
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("DVD_GEMM_V3"); v = s ? atoi(s) : 0; }
+  return v;
+}
 static bool force_v2() {
   static int v = -1;
   if (v < 0) { const char* s = getenv("DVD_GEMM_V2"); v = (s && s[0] == '1') ? 1 : 0; }
@@ -295,6 +302,11 @@ int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ld
   DVD_REQUIRE(A && W && (e.out || e.out_bf16), "gemm_tc: null pointer");
   DVD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && M % 128 == 0, "gemm_tc: bad shape M=%d N=%d K=%d (M must be a multiple of 128)", M, N, K);
   int rc = check_epilogue(e, N); if (rc) return rc;
+  if (v3_mode() == 1 && M % 256 == 0 && N % 128 == 0) {
+    int bn = (N % 256 == 0) ? 256 : 128;
+    if (const char* f = getenv("DVD_GEMM_BN")) { int v = atoi(f); if ((v == 128 || v == 256) && N % v == 0) bn = v; }
+    return gemm_tc3_dispatch(A, lda, W, ldw, M, N, K, e, bn, st);
+  }
   // Measured on B200 (profiles/r1_gemm_microbench.txt): the persistent 128x256 kernel wins once there are >= 4 waves of wide
   // tiles (1.1 PFLOP/s at M = 16384); the small M = 2048 problems of a single document are latency-bound and run faster as two
   // co-resident 128x128 CTAs per SM.
