@@ -24,7 +24,7 @@ template <int BN>
 struct QCfg {
   static constexpr int A_BYTES = QBM * QBK * 2, B_BYTES = (BN / 2) * QBK * 2;       // per CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int STAGES = (BN == 256) ? 3 : 4;       // <= 96 KB ring: two CTAs (of different pairs) per SM overlap epilogue and main loop
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int CW = 128;
   static constexpr int SLD = CW + 4;
@@ -72,7 +72,7 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
 }
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 2)
 k_gemm_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, Epilogue e) {
   using Cfg = QCfg<BN>;
   constexpr int ST = Cfg::STAGES;

@@ -70,7 +70,7 @@ class Schedule:
 
 def ddim_update(sch: Schedule, i: int, x: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
     """GD:470-489 with eta=0 (sigma=0, the drawn noise is multiplied by 0), op order as written."""
-    f = lambda v: torch.tensor(v, dtype=torch.float64).float()
+    f = lambda v: torch.tensor(v, dtype=torch.float64).float().to(x.device)
     eps = (f(sch.sqrt_recip_acp[i]) * x - pred) / f(sch.sqrt_recipm1_acp[i])
     abp = f(sch.acp_prev[i])
     return pred * torch.sqrt(abp) + torch.sqrt(1 - abp - 0.0) * eps
@@ -80,7 +80,7 @@ def ddim_update(sch: Schedule, i: int, x: torch.Tensor, pred: torch.Tensor) -> t
 def timestep_embedding(t: torch.Tensor, dim: int = 256, max_period: int = 10000) -> torch.Tensor:
     """CM:111-134 (cos ‖ sin)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -252,7 +252,7 @@ def denoiser_forward(sd, x, t_scaled: float, init_flow, init_feat, static: Stati
         static = Static(sd, y512, mask_cat, mask_y512, line_msk)
     rep = lambda v: v.expand(N, *v.shape[1:]) if v.shape[0] != N else v
     xe = patch_embed(sd, "obs", x)                                               # CM:571
-    temb = t_embed(sd, torch.full((N,), remap_t(t_scaled), dtype=torch.float32))  # CM:575-580
+    temb = t_embed(sd, torch.full((N,), remap_t(t_scaled), dtype=torch.float32, device=x.device))  # CM:575-580
     feat = rep(static.feat)
     if t_scaled > 600:                                                           # CM:597-598
         init_feat = feat
@@ -276,6 +276,7 @@ def base_grid(n: int) -> torch.Tensor:
 
 
 def grid_sample_ref(src, grid_nchw):
+    grid_nchw = grid_nchw.to(src.device)
     """WP:50-73 SpatialTransformer2.forward."""
     return F.grid_sample(src, grid_nchw.permute(0, 2, 3, 1), align_corners=True, mode="bilinear", padding_mode="zeros")
 
@@ -289,7 +290,7 @@ def sample(sd, inp: dict, S: int = 3, n_batch: int = 2, schedule: str = "cosine"
     rep = lambda v: v.repeat(n_batch, 1, 1, 1)                                   # GD:574
     init_flow, init_feat = rep(inp["init_flow"]), rep(inp["init_feat"])
     static = None if as_written else Static(sd, inp["y512"], inp["mask_cat"], inp["mask_y512"], inp["line_msk"])
-    b64 = base_grid(64)
+    b64 = base_grid(64).to(img.device)
     rec = {"pred": [], "x": [], "init_feat_cs": []}
     pred = feat = None
     for i in range(S - 1, -1, -1):                                               # GD:597
@@ -313,7 +314,7 @@ def sample(sd, inp: dict, S: int = 3, n_batch: int = 2, schedule: str = "cosine"
 def fullres_grid(map64: torch.Tensor, H: int, W: int) -> torch.Tensor:
     """EV:301-306: upsample map, upsample the 512^2 base ramp, affine 0.987."""
     s = F.interpolate(map64, size=(H, W), mode="bilinear", align_corners=True)
-    base = F.interpolate(base_grid(512), size=(H, W), mode="bilinear", align_corners=True)
+    base = F.interpolate(base_grid(512).to(map64.device), size=(H, W), mode="bilinear", align_corners=True)
     return ((s + base) * 1 * 2 - 1) * 0.987
 
 
