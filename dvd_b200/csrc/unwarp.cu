@@ -342,32 +342,38 @@ __global__ void __launch_bounds__(256) k_unwarp_fast(const void* __restrict__ ph
   }
   float res[C][4];
   if (__all_sync(0xffffffffu, inside) && jt0 + TILE_W <= W) {
-    // all-inside path: 32-bit unsigned element indices off ONE uniform base pointer (cheap address arithmetic)
+    // all-inside path.  Address arithmetic is kept to one 64-bit pointer per pixel plus one add per channel / row: the tap
+    // loads then use immediate offsets (profiles/r1_ncu_unwarp.txt showed ~6 integer instructions per load before this).
     if (IN_U8) {
       const uint8_t* __restrict__ ph = (const uint8_t*)photo_ + (size_t)b * plane * C;
+      const size_t rowb = (size_t)W * C;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        const uint32_t i0 = (uint32_t)off[p] * C, i1 = i0 + (uint32_t)W * C;
+        const uint8_t* q0 = ph + (size_t)off[p] * C;
+        const uint8_t* q1 = q0 + rowb;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          float v = (float)__ldg(ph + (i0 + c)) * wnw[p];
-          v += (float)__ldg(ph + (i0 + C + c)) * wne[p];
-          v += (float)__ldg(ph + (i1 + c)) * wsw[p];
-          v += (float)__ldg(ph + (i1 + C + c)) * wse[p];
+          float v = (float)__ldg(q0 + c) * wnw[p];
+          v += (float)__ldg(q0 + C + c) * wne[p];
+          v += (float)__ldg(q1 + c) * wsw[p];
+          v += (float)__ldg(q1 + C + c) * wse[p];
           res[c][p] = v;
         }
       }
     } else {
       const float* __restrict__ ph = (const float*)photo_ + (size_t)b * C * plane;
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
+      for (int p = 0; p < 4; ++p) {
+        const float* q0 = ph + off[p];
+        const float* q1 = q0 + W;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const uint32_t i0 = (uint32_t)(c * plane) + (uint32_t)off[p], i1 = i0 + (uint32_t)W;
-          float v = __ldg(ph + i0) * wnw[p];
-          v += __ldg(ph + (i0 + 1u)) * wne[p];
-          v += __ldg(ph + i1) * wsw[p];
-          v += __ldg(ph + (i1 + 1u)) * wse[p];
+        for (int c = 0; c < C; ++c) {
+          const float* a = q0 + (size_t)c * plane;
+          const float* d = q1 + (size_t)c * plane;
+          float v = __ldg(a) * wnw[p];
+          v += __ldg(a + 1) * wne[p];
+          v += __ldg(d) * wsw[p];
+          v += __ldg(d + 1) * wse[p];
           res[c][p] = v;
         }
       }
