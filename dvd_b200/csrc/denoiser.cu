@@ -172,16 +172,16 @@ static int static_forward(const Ctx& c, const float* y512, const float* mask_cat
   // ---- K1 pyramid (CM:83-95): 7 x conv3x3+ReLU, 3 x maxpool, NHWC
   DVD_TRY(pack_y4(y512, mask_cat, s.y4, B, st));
   if (c.tc()) {
-    // level_0 (Cin = 4, K = 36) stays on the FFMA path and emits bf16 NHWC; the six wide convs run as implicit GEMMs on
-    // tcgen05 with bf16 activations; the last pool writes the fp32 feature map the rest of the model consumes.
+    // level_0 (Cin = 4): the 3x3x4 patch of every pixel is written once as a K = 64 (36 valid + zero padding) bf16 row
+    // (im2col, 128 B per pixel) and multiplied by the K-padded weight on tcgen05; the six wide convs run as implicit GEMMs
+    // directly on the NHWC activations; the last pool writes the fp32 feature map the rest of the model consumes.
     __nv_bfloat16 *P = (__nv_bfloat16*)s.pyrP, *Q = (__nv_bfloat16*)s.pyrQ;
     {
       ProfScope ps(PC_CONV, st, 2.0 * B * 512 * 512 * 64 * 36.0);
-      GemmParams p;
-      p.A = s.y4; p.convH = 512; p.convW = 512; p.convC = 4;
-      p.B = w.pyr[0].f32; p.ldb = 36; p.M = B * 512 * 512; p.N = 64; p.K = 36;
-      p.e.bias = w.pyr_b[0]; p.e.act = ACT_RELU; p.e.out_bf16 = P; p.e.ldc_bf16 = 64;
-      DVD_TRY(gemm_f32(p, A_CONV3, B_NK, 1, st));
+      DVD_REQUIRE(w.pyr[0].bf16, "pyramid level_0 bf16 (K-padded) weight missing");
+      DVD_TRY(im2col3x3_c4_bf16(s.y4, Q, B, 512, 512, st));                       // Q: [B*512*512, 64] bf16
+      Epilogue e; e.bias = w.pyr_b[0]; e.act = ACT_RELU; e.out_bf16 = P; e.ldc_bf16 = 64;
+      DVD_TRY(gemm_tc_bf16(Q, 64, (const __nv_bfloat16*)w.pyr[0].bf16, 64, B * 512 * 512, 64, 64, e, st));
     }
     auto conv = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int H, int Cin, int layer) -> int {
       const int Cout = w.pyr[layer].n;

@@ -96,6 +96,38 @@ int maxpool2_nhwc(const float* in, float* out, int B, int H, int W, int C, cudaS
   return 0;
 }
 
+// one thread = one (pixel, tap pair): 8 of the 16-byte chunks of a 128-byte output row; chunks 5..7 (k >= 40) are zero and
+// chunk 4 holds tap 8 + zeros
+__global__ void __launch_bounds__(256) k_im2col_c4(const float4* __restrict__ in, uint4* __restrict__ out, int H, int W, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // total = B*H*W*8 chunks
+  if (i >= total) return;
+  const int chunk = i & 7; const size_t pix = i >> 3;
+  const int x = pix % W; const int y = (pix / W) % H; const size_t b = pix / ((size_t)W * H);
+  float4 v[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int tap = chunk * 2 + t;
+    v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tap < 9) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v[t] = __ldg(in + (b * H + yy) * W + xx);
+    }
+  }
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0].x, v[0].y), p1 = __floats2bfloat162_rn(v[0].z, v[0].w);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[1].x, v[1].y), p3 = __floats2bfloat162_rn(v[1].z, v[1].w);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+  o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+  out[i] = o;
+}
+int im2col3x3_c4_bf16(const float* in, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st) {
+  DVD_REQUIRE(in && out && B > 0, "im2col: bad args");
+  size_t total = (size_t)B * H * W * 8;
+  k_im2col_c4<<<cdiv(total, 256), 256, 0, st>>>((const float4*)in, (uint4*)out, H, W, total);
+  DVD_LAUNCH_CHECK("k_im2col_c4");
+  return 0;
+}
+
 // 2x2 max pool on bf16 NHWC (8 channels = 16 bytes per thread); writes bf16 and/or fp32
 __global__ void k_maxpool2_bf16(const uint4* __restrict__ in, uint4* __restrict__ out16, float* __restrict__ out32, int B, int H, int W, int C8) {
   const int Ho = H / 2, Wo = W / 2;

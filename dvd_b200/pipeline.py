@@ -46,49 +46,74 @@ class DewarpPipeline:
         self.use_graph = os.environ.get("DVD_NO_GRAPH", "0") != "1"
         self._graphs = {}                  # input-pointer tuple -> (CUDAGraph, kernels per replay, keep-alive dict)
         self.kernel_launches = 0           # kernels of libdvd_b200 launched (or replayed) through this pipeline
+        self._copy_stream = None
+        self._photo_ready = None
 
     # ---- device-resident inputs: dict with y512, mask_cat, mask_y512, line_msk, x_T, photo_u8 (all on self.dev)
-    def _enqueue(self, d: dict):
-        """static conditioning -> S-step DDIM loop -> hypothesis mean -> fused upsample+unwarp, all on the current stream."""
-        st = _lib.stream_ptr()
+    def _enqueue_sampling(self, d: dict):
+        """static conditioning -> S-step DDIM loop -> hypothesis mean (map64), on the current stream."""
         self.eng.static_forward(d["y512"], d["mask_cat"], d["mask_y512"], d["line_msk"])
         self.eng.sample(d["x_T"], self.init_flow0, self.tables, self.t_scaled, self.a, self.b, None, self.map64)
+
+    def _enqueue_unwarp(self, d: dict):
+        """fused upsample + affine + bilinear unwarp of the full-resolution photo, on the current stream."""
         _lib.check(self.lib.dvd_unwarp_u8(_lib.ptr(d["photo_u8"]), _lib.ptr(self.map64), _lib.ptr(self.out_u8), self.docs, 3,
-                                          self.H, self.W, 64, 64, AFFINE, st), "dvd_unwarp_u8")
+                                          self.H, self.W, 64, 64, AFFINE, _lib.stream_ptr()), "dvd_unwarp_u8")
+
+    def _graph(self, which: str, d: dict, keys, fn):
+        """CUDA graph of `fn(d)` for this set of input buffers (captured once, replayed afterwards)."""
+        key = (which,) + tuple(d[k].data_ptr() for k in keys)
+        if key not in self._graphs:
+            fn(d)                                                  # eager warm-up (function attributes, driver entry points)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = self.lib.dvd_launch_count(0)
+            with torch.cuda.graph(g):
+                fn(d)
+            if len(self._graphs) >= 16:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = (g, self.lib.dvd_launch_count(0) - n0, d)
+        return self._graphs[key]
+
+    def _run(self, which: str, d: dict, keys, fn):
+        if not self.use_graph:
+            n0 = self.lib.dvd_launch_count(0)
+            fn(d)
+            self.kernel_launches += self.lib.dvd_launch_count(0) - n0
+            return
+        g, n, _ = self._graph(which, d, keys, fn)
+        g.replay()
+        self.kernel_launches += n
+
+    SAMPLING_KEYS = ("y512", "mask_cat", "mask_y512", "line_msk", "x_T")
 
     def run_device(self, d: dict) -> torch.Tensor:
-        """The ~300 kernel launches of one batch are captured once per set of input buffers into a CUDA graph and replayed
-        (the library never allocates or synchronises, so every entry point is capturable)."""
+        """The ~245 kernel launches of one batch are captured once per set of input buffers into two CUDA graphs (sampling,
+        unwarp) and replayed (the library never allocates or synchronises, so every entry point is capturable)."""
         with torch.cuda.device(self.dev):
-            if not self.use_graph:
-                n0 = self.lib.dvd_launch_count(0)
-                self._enqueue(d)
-                self.kernel_launches += self.lib.dvd_launch_count(0) - n0
-                return self.out_u8
-            key = tuple(d[k].data_ptr() for k in ("y512", "mask_cat", "mask_y512", "line_msk", "x_T", "photo_u8"))
-            if key not in self._graphs:
-                self._enqueue(d)                                   # eager warm-up (function attributes, driver entry points)
-                torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                n0 = self.lib.dvd_launch_count(0)
-                with torch.cuda.graph(g):
-                    self._enqueue(d)
-                if len(self._graphs) >= 8:
-                    self._graphs.pop(next(iter(self._graphs)))
-                self._graphs[key] = (g, self.lib.dvd_launch_count(0) - n0, d)
-            g, n, _ = self._graphs[key]
-            g.replay()
-            self.kernel_launches += n
+            self._run("sampling", d, self.SAMPLING_KEYS, self._enqueue_sampling)
+            self._run("unwarp", d, ("photo_u8",), self._enqueue_unwarp)
         return self.out_u8
 
     # ---- pinned-host inputs -> host uint8 image (H2D and D2H inside the call)
     def run_host(self, h: dict) -> torch.Tensor:
+        """The photo is only needed by the last kernel, so its upload runs on a second stream underneath the sampling graph."""
         with torch.cuda.device(self.dev):
-            for k, v in self.buf.items():
-                v.copy_(h[k], non_blocking=True)
-            self.run_device(self.buf)
+            main = torch.cuda.current_stream()
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.dev)
+                self._photo_ready = torch.cuda.Event()
+            for k in self.SAMPLING_KEYS:
+                self.buf[k].copy_(h[k], non_blocking=True)
+            self._copy_stream.wait_stream(main)                    # the previous call's unwarp has finished reading photo_u8
+            with torch.cuda.stream(self._copy_stream):
+                self.buf["photo_u8"].copy_(h["photo_u8"], non_blocking=True)
+                self._photo_ready.record()
+            self._run("sampling", self.buf, self.SAMPLING_KEYS, self._enqueue_sampling)
+            main.wait_event(self._photo_ready)
+            self._run("unwarp", self.buf, ("photo_u8",), self._enqueue_unwarp)
             self.out_host.copy_(self.out_u8, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            main.synchronize()
         return self.out_host
 
     # ---- measurement helpers used by bench.py

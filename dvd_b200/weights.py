@@ -93,6 +93,11 @@ class PackedWeights:
         for i, p in enumerate(PYR_KEYS):
             w = sd[p + ".weight"].float()                                  # [Cout, Cin, 3, 3] -> [Cout, ky, kx, Cin]
             T.pyr[i] = self._mat(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), bf16=(i > 0))
+            if i == 0 and self.with_bf16:                                   # level_0: K = 36 zero-padded to 64 for the tcgen05 im2col GEMM
+                pad = torch.zeros((w.shape[0], 64), dtype=torch.bfloat16, device=self.device)
+                pad[:, :36] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(self.device).to(torch.bfloat16)
+                self.keep.append(pad)
+                T.pyr[0].bf16 = pad.data_ptr()
             T.pyr_b[i] = self._vec(sd[p + ".bias"])
         for i, e in enumerate(EMB_KEYS):
             w = sd[f"{e}_embedder.proj.weight"].float()
