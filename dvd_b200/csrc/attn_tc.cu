@@ -14,6 +14,7 @@
 // d in {64, 256}; T a multiple of 128.
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
+#include <string.h>
 
 namespace dvd {
 using namespace tc;
@@ -45,10 +46,18 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Up to ACTX independent key/value contexts share one launch (the four cross-attention contexts of the DiT block use the same
+// queries): blockIdx.z = ctx * nsamp + sample.  Each context has its own K / V^T tensor maps, kv_div and output base.
+constexpr int ACTX = 4;
+struct AttnCtx {
+  CUtensorMap tmK[ACTX], tmVt[ACTX];
+  __nv_bfloat16* out[ACTX];
+  int kv_div[ACTX];
+};
+
 template <int D>
-__global__ void __launch_bounds__(ATHREADS) k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                                                      const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ O, int ldo, int T,
-                                                      int heads, int kv_div, float scale_log2) {
+__global__ void __launch_bounds__(ATHREADS) k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ AttnCtx cx, int nsamp,
+                                                      int ldo, int T, int heads, float scale_log2) {
   using Cfg = AttnCfg<D>;
   constexpr int ST = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -70,8 +79,12 @@ __global__ void __launch_bounds__(ATHREADS) k_attn_tc(const __grid_constant__ CU
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * AQ, h = blockIdx.y, n = blockIdx.z, nkv = n / kv_div;
+  const int ctx = blockIdx.z / nsamp;
+  const int q0 = blockIdx.x * AQ, h = blockIdx.y, n = blockIdx.z - ctx * nsamp, nkv = n / cx.kv_div[ctx];
   const int nt = T / AKV;
+  const CUtensorMap& tmK = cx.tmK[ctx];
+  const CUtensorMap& tmVt = cx.tmVt[ctx];
+  __nv_bfloat16* __restrict__ O = cx.out[ctx];
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmVt);
@@ -255,16 +268,8 @@ int transpose_v_bf16(const __nv_bfloat16* v, int ldv, __nv_bfloat16* vt, int nsa
   return 0;
 }
 
-int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt, __nv_bfloat16* o, int ldo,
-                      int nsamp, int heads, int T, int d, float scale, int kv_div, cudaStream_t st) {
-  DVD_REQUIRE(q && k && vt && o, "attention_tc: null pointer");
-  DVD_REQUIRE((d == 64 || d == 256) && T % 128 == 0 && nsamp > 0 && kv_div > 0 && nsamp % kv_div == 0, "attention_tc: bad shape d=%d T=%d", d, T);
-  DVD_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention_tc: output must be 16-byte aligned");
-  const int nkv = nsamp / kv_div;
-  CUtensorMap tmQ, tmK, tmVt;
-  int rc = make_tmap_bf16_2d(&tmQ, q, (uint64_t)nsamp * T, (uint64_t)heads * d, (uint64_t)ldq, AQ, 64); if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmK, k, (uint64_t)nkv * T, (uint64_t)heads * d, (uint64_t)ldk, AKV, 64); if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmVt, vt, (uint64_t)nkv * heads * d, (uint64_t)T, (uint64_t)T, d, 64); if (rc) return rc;
+static int launch_attention(const CUtensorMap& tmQ, const AttnCtx& cx, int nctx, int ldo, int nsamp, int heads, int T, int d, float scale,
+                            cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     DVD_CUDA(cudaFuncSetAttribute(k_attn_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::SMEM));
@@ -272,11 +277,39 @@ int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, i
     attr_set = true;
   }
   const float scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid(T / AQ, heads, nsamp);
-  if (d == 64) k_attn_tc<64><<<grid, ATHREADS, AttnCfg<64>::SMEM, st>>>(tmQ, tmK, tmVt, o, ldo, T, heads, kv_div, scale_log2);
-  else         k_attn_tc<256><<<grid, ATHREADS, AttnCfg<256>::SMEM, st>>>(tmQ, tmK, tmVt, o, ldo, T, heads, kv_div, scale_log2);
+  dim3 grid(T / AQ, heads, nsamp * nctx);
+  if (d == 64) k_attn_tc<64><<<grid, ATHREADS, AttnCfg<64>::SMEM, st>>>(tmQ, cx, nsamp, ldo, T, heads, scale_log2);
+  else         k_attn_tc<256><<<grid, ATHREADS, AttnCfg<256>::SMEM, st>>>(tmQ, cx, nsamp, ldo, T, heads, scale_log2);
   DVD_LAUNCH_CHECK("k_attn_tc");
   return 0;
+}
+
+// nctx (<= 4) key/value contexts attended by the SAME queries in one launch; k[i]/vt[i]/o[i]/kv_div[i] describe context i.
+int attention_tc_bf16_multi(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* const* k, int ldk, const __nv_bfloat16* const* vt,
+                            __nv_bfloat16* const* o, int ldo, const int* kv_div, int nctx, int nsamp, int heads, int T, int d, float scale,
+                            cudaStream_t st) {
+  DVD_REQUIRE(q && k && vt && o && kv_div && nctx >= 1 && nctx <= ACTX, "attention_tc_multi: bad arguments");
+  DVD_REQUIRE((d == 64 || d == 256) && T % 128 == 0 && nsamp > 0, "attention_tc: bad shape d=%d T=%d", d, T);
+  DVD_REQUIRE(ldo % 8 == 0 && (long long)nsamp * nctx <= 65535, "attention_tc: bad ldo / batch");
+  CUtensorMap tmQ;
+  AttnCtx cx;
+  memset(&cx, 0, sizeof(cx));
+  int rc = make_tmap_bf16_2d(&tmQ, q, (uint64_t)nsamp * T, (uint64_t)heads * d, (uint64_t)ldq, AQ, 64); if (rc) return rc;
+  for (int i = 0; i < nctx; ++i) {
+    DVD_REQUIRE(k[i] && vt[i] && o[i] && kv_div[i] > 0 && nsamp % kv_div[i] == 0 && (reinterpret_cast<uintptr_t>(o[i]) & 15) == 0,
+                "attention_tc: bad context %d", i);
+    const int nkv = nsamp / kv_div[i];
+    rc = make_tmap_bf16_2d(&cx.tmK[i], k[i], (uint64_t)nkv * T, (uint64_t)heads * d, (uint64_t)ldk, AKV, 64); if (rc) return rc;
+    rc = make_tmap_bf16_2d(&cx.tmVt[i], vt[i], (uint64_t)nkv * heads * d, (uint64_t)T, (uint64_t)T, d, 64); if (rc) return rc;
+    cx.out[i] = o[i]; cx.kv_div[i] = kv_div[i];
+  }
+  return launch_attention(tmQ, cx, nctx, ldo, nsamp, heads, T, d, scale, st);
+}
+
+int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt, __nv_bfloat16* o, int ldo,
+                      int nsamp, int heads, int T, int d, float scale, int kv_div, cudaStream_t st) {
+  DVD_REQUIRE(q && k && vt && o, "attention_tc: null pointer");
+  return attention_tc_bf16_multi(q, ldq, &k, ldk, &vt, &o, ldo, &kv_div, 1, nsamp, heads, T, d, scale, st);
 }
 
 }  // namespace dvd

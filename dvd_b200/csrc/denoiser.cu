@@ -264,12 +264,20 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     if (tc) { ek.vt_out = s.vt_r16; ek.vt_col0 = 384; }
     DVD_TRY(linear(c, s.r, s.r16, 384, w.xattn_in, 384, M, 768, ek));
   }
-  for (int i = 0; i < 4; ++i) {                  // stream order x1..x4 = cond, msk6, msk_line, r  (CM:243-265)
-    const float* kv = i < 3 ? s.kv_static[i] : s.kv_r;
-    const __nv_bfloat16* kv16 = tc ? (i < 3 ? s.kv_static16[i] : s.kv_r16) : nullptr;
-    const __nv_bfloat16* vt16 = tc ? (i < 3 ? s.vt_static16[i] : s.vt_r16) : nullptr;
-    DVD_TRY(attention(c, s.q, s.q16, 384, kv, kv16, 768, kv + 384, vt16, 768, s.xo + (size_t)i * M * 384,
-                      tc ? s.xo16 + (size_t)i * M * 384 : nullptr, 384, N, 64, 0.125f, i < 3 ? c.n_hyp : 1));
+  if (tc) {
+    // the four contexts (stream order x1..x4 = cond, msk6, msk_line, r; CM:243-265) share the queries: ONE launch of 4 x N x 6 x 8 CTAs
+    ProfScope ps(PC_ATTN, st, 4.0 * 4.0 * N * kHeads * 1024.0 * 1024.0 * 64);
+    const __nv_bfloat16* kk[4] = {s.kv_static16[0], s.kv_static16[1], s.kv_static16[2], s.kv_r16};
+    const __nv_bfloat16* vv[4] = {s.vt_static16[0], s.vt_static16[1], s.vt_static16[2], s.vt_r16};
+    __nv_bfloat16* oo[4] = {s.xo16, s.xo16 + (size_t)M * 384, s.xo16 + (size_t)2 * M * 384, s.xo16 + (size_t)3 * M * 384};
+    const int dv[4] = {c.n_hyp, c.n_hyp, c.n_hyp, 1};
+    DVD_TRY(attention_tc_bf16_multi(s.q16, 384, kk, 768, vv, oo, 384, dv, 4, N, kHeads, 1024, 64, 0.125f, st));
+  } else {
+    for (int i = 0; i < 4; ++i) {                // stream order x1..x4 = cond, msk6, msk_line, r  (CM:243-265)
+      const float* kv = i < 3 ? s.kv_static[i] : s.kv_r;
+      DVD_TRY(attention(c, s.q, nullptr, 384, kv, nullptr, 768, kv + 384, nullptr, 768, s.xo + (size_t)i * M * 384, nullptr, 384, N, 64,
+                        0.125f, i < 3 ? c.n_hyp : 1));
+    }
   }
   {
     Epilogue e; e.bias = w.xattn_out_b; e.resid = s.xe; e.ldr = 384; e.resid_mod = M; e.out = s.xs; e.ldc = 384;

@@ -21,6 +21,11 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* Wt, int B, int
 int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt, __nv_bfloat16* o, int ldo,
                       int nsamp, int heads, int T, int d, float scale, int kv_div, cudaStream_t st);
 
+// Same, for up to 4 key/value contexts that share the queries (one launch): context i uses k[i], vt[i], kv_div[i], writes o[i].
+int attention_tc_bf16_multi(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* const* k, int ldk, const __nv_bfloat16* const* vt,
+                            __nv_bfloat16* const* o, int ldo, const int* kv_div, int nctx, int nsamp, int heads, int T, int d, float scale,
+                            cudaStream_t st);
+
 // V [nsamp, T, C] (row stride ldv) -> V^T [nsamp, C, T]  (test hook only)
 int transpose_v_bf16(const __nv_bfloat16* v, int ldv, __nv_bfloat16* vt, int nsamp, int T, int C, cudaStream_t st);
 

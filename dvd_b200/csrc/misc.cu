@@ -374,14 +374,23 @@ __global__ void __launch_bounds__(256) k_gemv(const float* __restrict__ in, int 
   for (int r = 0; r < GEMV_MAXR; ++r) acc[r] = 0.f;
   const float4* wr = reinterpret_cast<const float4*>(W + (size_t)j * K);
   const int K4 = K >> 2;
-#pragma unroll 4
-  for (int k = lane; k < K4; k += 32) {
-    const float4 wv = __ldg(wr + k);
+  // the whole weight row of this output (<= 12 x 16 bytes per lane for K <= 1536) is requested before any use
+  float4 wv[12];
 #pragma unroll
-    for (int r = 0; r < GEMV_MAXR; ++r) {
-      if (r < rows) {
-        const float4 x = *reinterpret_cast<const float4*>(xs + r * K + 4 * k);
-        acc[r] += (wv.x * x.x + wv.y * x.y) + (wv.z * x.z + wv.w * x.w);
+  for (int i = 0; i < 12; ++i) {
+    const int k = lane + 32 * i;
+    wv[i] = (k < K4) ? __ldg(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int k = lane + 32 * i;
+    if (k < K4) {
+#pragma unroll
+      for (int r = 0; r < GEMV_MAXR; ++r) {
+        if (r < rows) {
+          const float4 x = *reinterpret_cast<const float4*>(xs + r * K + 4 * k);
+          acc[r] += (wv[i].x * x.x + wv[i].y * x.y) + (wv[i].z * x.z + wv[i].w * x.w);
+        }
       }
     }
   }
