@@ -1,6 +1,7 @@
 // C-ABI plumbing: version, thread-local error text, device check, launch counter, test hooks.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "misc.cuh"
@@ -21,6 +22,15 @@ int cuda_fail(cudaError_t e, const char* what) {
   return (int)e;
 }
 void count_launch(int n) { g_launches += n; }
+bool pdl_enabled(int kind) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* off = getenv("DVD_NO_PDL");
+    const char* m = getenv("DVD_PDL_MASK");
+    mask = (off && off[0] == '1') ? 0 : (m ? atoi(m) : 0xF);
+  }
+  return (mask & kind) != 0;
+}
 
 }  // namespace dvd
 

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(ATHREADS) k_attn_tc(const __grid_constant__ CU
   const CUtensorMap& tmVt = cx.tmVt[ctx];
   __nv_bfloat16* __restrict__ O = cx.out[ctx];
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmVt);
     mbar_init(q_full, 1);
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(ATHREADS) k_attn_tc(const __grid_constant__ CU
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -278,8 +280,8 @@ static int launch_attention(const CUtensorMap& tmQ, const AttnCtx& cx, int nctx,
   }
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(T / AQ, heads, nsamp * nctx);
-  if (d == 64) k_attn_tc<64><<<grid, ATHREADS, AttnCfg<64>::SMEM, st>>>(tmQ, cx, nsamp, ldo, T, heads, scale_log2);
-  else         k_attn_tc<256><<<grid, ATHREADS, AttnCfg<256>::SMEM, st>>>(tmQ, cx, nsamp, ldo, T, heads, scale_log2);
+  if (d == 64) DVD_CUDA(launch_pdl(2, k_attn_tc<64>, grid, dim3(ATHREADS), (size_t)AttnCfg<64>::SMEM, st, tmQ, cx, nsamp, ldo, T, heads, scale_log2));
+  else         DVD_CUDA(launch_pdl(2, k_attn_tc<256>, grid, dim3(ATHREADS), (size_t)AttnCfg<256>::SMEM, st, tmQ, cx, nsamp, ldo, T, heads, scale_log2));
   DVD_LAUNCH_CHECK("k_attn_tc");
   return 0;
 }

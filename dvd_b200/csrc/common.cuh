@@ -44,6 +44,26 @@ constexpr int kDec = 1536;           // decoder d_model
 constexpr int kDecInner = 2048;
 constexpr int kHeads = 6;
 
+// ---- programmatic dependent launch (PDL) ----
+// Kernels launched through launch_pdl() may begin (prologue: barrier init, TMEM allocation, descriptor prefetch) while the
+// previous kernel of the stream is still draining; they call pdl_wait() before touching any global memory the predecessor
+// may have written, and pdl_trigger() at their start so that THEIR successor can be scheduled early.  Set DVD_NO_PDL=1 to
+// fall back to plain stream serialisation.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled(int kind = 0xF);     // kind: 1 = GEMM, 2 = attention, 4 = layer norm, 8 = depthwise conv (DVD_PDL_MASK selects)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled(kind) ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -71,7 +71,8 @@ constexpr int TBM = 128, TBK = 64;
 
 template <int BN>
 struct TcCfg {
-  static constexpr int STAGES = (BN == 64) ? 4 : ((BN == 128) ? 3 : 2);   // <= 96 KB of ring -> two CTAs per SM
+  static constexpr int STAGES = (BN == 64) ? 4 : ((BN <= 128) ? 3 : 2);   // <= 96 KB of ring -> two CTAs per SM
+  static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // power of two >= BN
   static constexpr int A_BYTES = TBM * TBK * 2, B_BYTES = BN * TBK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CW = BN < 128 ? BN : 128;                          // columns per epilogue pass
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
   const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
   const int nkb = (K + TBK - 1) / TBK;
 
+  pdl_trigger();                                        // the next kernel of the stream may start its own prologue
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -107,11 +109,12 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);            // BN fp32 accumulator columns (power of two >= 32)
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                           // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 template <int BN, bool CONV>
@@ -261,7 +264,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
     attr_set = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, TBM));
-  k_gemm_tc<BN, CONV><<<grid, 128, TcCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, e, cg);
+  DVD_CUDA(launch_pdl(1, k_gemm_tc<BN, CONV>, grid, dim3(128), (size_t)TcCfg<BN>::SMEM, st, tmA, tmB, M, N, K, e, cg));
   DVD_LAUNCH_CHECK("k_gemm_tc");
   return 0;
 }
@@ -315,10 +318,15 @@ int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ld
   // wide tiles only when they still fill the machine (>= ~1 wave of 2 CTAs/SM)
   const bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) >= 2 * kSMs);
   const bool narrow = (N <= 64);
+  // 128x96 tiles were measured (tools/gemm_bench.py, DVD_GEMM_BN=96): no gain over 128x128 on the N = 1536 shapes (23.5 vs 23.6 us:
+  // those launches are bound by the fixed prologue/epilogue cost, not by SM balance), so they are only reachable for experiments.
+  bool bn96 = false;
+  if (const char* f = getenv("DVD_GEMM_BN")) bn96 = (atoi(f) == 96) && !wide && !narrow && N % 96 == 0;
   CUtensorMap tmA, tmB;
   rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64); if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, narrow ? 64 : 128, 64); if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, narrow ? 64 : (bn96 ? 96 : 128), 64); if (rc) return rc;
   ConvGeom cg{0, 0, 0};
+  if (bn96 && !wide) return launch_tc<96, false>(tmA, tmB, M, N, K, e, cg, st);
   if (wide) return launch_tc<256, false>(tmA, tmB, M, N, K, e, cg, st);
   if (narrow) return launch_tc<64, false>(tmA, tmB, M, N, K, e, cg, st);
   return launch_tc<128, false>(tmA, tmB, M, N, K, e, cg, st);

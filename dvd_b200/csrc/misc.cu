@@ -8,6 +8,8 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ in,
                                                    __nv_bfloat16* __restrict__ out16, int ldo16, int rows, float eps,
                                                    const float* __restrict__ w, const float* __restrict__ b,
                                                    const float* __restrict__ msh, const float* __restrict__ msc) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   constexpr int C = 128 * NV;
@@ -52,8 +54,8 @@ int layernorm(const float* in, int ldin, float* out, int ldo, __nv_bfloat16* out
   DVD_REQUIRE(C == 384 || C == 1536, "layernorm: C must be 384 or 1536 (got %d)", C);
   DVD_REQUIRE(ldin % 4 == 0 && ldo % 4 == 0 && ldo16 % 4 == 0, "layernorm: ld %% 4");
   dim3 grid(cdiv(rows, 8));
-  if (C == 384) k_layernorm<3><<<grid, 256, 0, st>>>(in, ldin, out, ldo, out16, ldo16, rows, eps, w, b, msh, msc);
-  else          k_layernorm<12><<<grid, 256, 0, st>>>(in, ldin, out, ldo, out16, ldo16, rows, eps, w, b, msh, msc);
+  if (C == 384) DVD_CUDA(launch_pdl(4, k_layernorm<3>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, ldo16, rows, eps, w, b, msh, msc));
+  else          DVD_CUDA(launch_pdl(4, k_layernorm<12>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, ldo16, rows, eps, w, b, msh, msc));
   DVD_LAUNCH_CHECK("k_layernorm");
   return 0;
 }
@@ -518,6 +520,8 @@ __global__ void __launch_bounds__(256) k_dwconv(const float4* __restrict__ in, c
 // bf16 in / bf16 out variant for the tensor path: 8 channels (16 bytes) per thread, fp32 accumulation
 __global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ sc,
                                                      const float* __restrict__ sh, uint4* __restrict__ out, int C8, size_t total) {
+  pdl_trigger();
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = i % C8; const size_t row = i / C8;
@@ -561,7 +565,7 @@ int dwconv3x3_bn_relu_bf16(const __nv_bfloat16* in, const float* w9c, const floa
                            cudaStream_t st) {
   DVD_REQUIRE(in && w9c && scale && shift && out && C % 8 == 0, "dwconv_bf16: bad args");
   size_t total = (size_t)N * 1024 * (C / 8);
-  k_dwconv_bf16<<<cdiv(total, 256), 256, 0, st>>>((const uint4*)in, w9c, scale, shift, (uint4*)out, C / 8, total);
+  DVD_CUDA(launch_pdl(8, k_dwconv_bf16, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, (const uint4*)in, w9c, scale, shift, (uint4*)out, C / 8, total));
   DVD_LAUNCH_CHECK("k_dwconv_bf16");
   return 0;
 }
