@@ -316,7 +316,8 @@ int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ld
   if (!use_v1() && (force_v2() || (N % 256 == 0 && (long long)(M / 128) * (N / 256) >= 4 * kSMs)))
     return gemm_tc2_dispatch(A, lda, W, ldw, M, N, K, e, 0, 0, 0, 0, st);
   // wide tiles only when they still fill the machine (>= ~1 wave of 2 CTAs/SM)
-  const bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) >= 2 * kSMs);
+  bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) * 100 >= 190LL * kSMs);   // >= ~1.9 SM-fulls of 128x256 tiles (2 CTAs/SM)
+  if (const char* f = getenv("DVD_GEMM_WIDE")) wide = (N % 256 == 0) && atoi(f) == 1;     // tuning override
   const bool narrow = (N <= 64);
   // 128x96 tiles were measured (tools/gemm_bench.py, DVD_GEMM_BN=96): no gain over 128x128 on the N = 1536 shapes (23.5 vs 23.6 us:
   // those launches are bound by the fixed prologue/epilogue cost, not by SM balance), so they are only reachable for experiments.
