@@ -66,6 +66,27 @@ int make_tmap_bf16_nhwc(CUtensorMap* out, const void* base, uint64_t n, uint64_t
   return 0;
 }
 
+// Plain (unswizzled) 3-D tile map over an image stack: dims {w, h, planes} of `elem_bytes`-sized elements (4 = fp32, 1 = uint8),
+// box {box_w, box_h, box_p}.  Used by the unwarp kernel to stage source windows; OOB elements are zero-filled (= zeros padding).
+int make_tmap_image3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t w, uint64_t h, uint64_t planes, uint32_t box_w,
+                      uint32_t box_h, uint32_t box_p) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return DVD_E_NOTMA; }
+  DVD_REQUIRE(elem_bytes == 4 || elem_bytes == 1, "image tensor map: fp32 or uint8 only");
+  DVD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (w * elem_bytes) % 16 == 0 && (box_w * elem_bytes) % 16 == 0 && box_w <= 256 &&
+                  box_h <= 256 && box_p <= 256, "image tensor map: alignment / box limits");
+  cuuint64_t gdim[3] = {w, h, planes};
+  cuuint64_t gstr[2] = {w * elem_bytes, w * h * elem_bytes};
+  cuuint32_t box[3] = {box_w, box_h, box_p};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (image) failed (%d) w=%llu h=%llu", (int)r, (unsigned long long)w,
+                                     (unsigned long long)h); return DVD_E_NOTMA; }
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------- kernel
 constexpr int TBM = 128, TBK = 64;
 
