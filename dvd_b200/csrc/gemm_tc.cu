@@ -80,7 +80,7 @@ int make_tmap_image3d(CUtensorMap* out, const void* base, int elem_bytes, uint64
   cuuint32_t box[3] = {box_w, box_h, box_p};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim,
-                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (image) failed (%d) w=%llu h=%llu", (int)r, (unsigned long long)w,
                                      (unsigned long long)h); return DVD_E_NOTMA; }

@@ -142,24 +142,33 @@ def test_unwarp_staged_and_gather_tiles_agree_with_oracle(dev, deg, zoom):
     pu8 = photo[0].permute(1, 2, 0).to(torch.uint8).unsqueeze(0).contiguous().to(dev)
     u8 = dewarp_fullres(m.to(dev), pu8).cpu()
     f32_u8 = dewarp_fullres(m.to(dev), photo.to(dev), out_uint8=True).cpu()
-    assert torch.equal(u8, f32_u8)
+    # uint8 photos run on the gather kernel, fp32 photos on the TMA-staged one: ulp-level coordinate differences -> rare 1-LSB flips
+    d8 = (u8.int() - f32_u8.int()).abs()
+    assert int(d8.max()) <= 1 and float((d8 != 0).float().mean()) < 0.01
     assert int((u8[0].int() - ref[0].permute(1, 2, 0).clamp(0, 255).int()).abs().max()) <= 1
 
 
 def test_unwarp_tma_and_gather_kernels_agree(dev):
-    """DVD_UNWARP_NO_TMA=1 (global-gather kernel) and the TMA-staged kernel give the same image (<= 1 ulp-level differences)."""
+    """The TMA-staged kernel (default for fp32 photos, DVD_UNWARP_TMA_U8=1 for uint8 photos) and the global-gather kernel
+    (DVD_UNWARP_NO_TMA=1) give the same image up to ulp-level coordinate differences."""
     import subprocess, sys, tempfile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = ("import sys, torch, numpy as np; sys.path.insert(0, %r); from oracle import synth; from dvd_b200 import dewarp_fullres\n"
-            "m = synth.make_map64(5, 'smooth').cuda(); p = synth.make_photo(1500, 2000, 21, 'page').cuda()\n"
-            "np.save(sys.argv[1], dewarp_fullres(m, p).cpu().numpy())\n" % root)
+            "m = synth.make_map64(5, 'smooth', amp=0.02).cuda(); p = synth.make_photo(1500, 2000, 21, 'page').cuda()\n"
+            "pu8 = p[0].permute(1, 2, 0).to(torch.uint8).unsqueeze(0).contiguous()\n"
+            "np.savez(sys.argv[1], f32=dewarp_fullres(m, p).cpu().numpy(), u8=dewarp_fullres(m, pu8).cpu().numpy(),"
+            " mixed=dewarp_fullres(m, p, out_uint8=True).cpu().numpy())\n" % root)
     outs = []
     with tempfile.TemporaryDirectory() as td:
-        for flag in ("0", "1"):
-            f = os.path.join(td, "o%s.npy" % flag)
-            subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, DVD_UNWARP_NO_TMA=flag), timeout=600)
-            outs.append(np.load(f))
-    assert float(np.abs(outs[0] - outs[1]).max()) < 0.25 and float(np.abs(outs[0] - outs[1]).mean()) < 1e-3   # ulp-level coordinate differences x page edges
+        for k, env in enumerate(({"DVD_UNWARP_NO_TMA": "1"}, {"DVD_UNWARP_TMA_U8": "1"})):
+            f = os.path.join(td, "o%d.npz" % k)
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, **env), timeout=600)
+            outs.append(dict(np.load(f)))
+    d = np.abs(outs[0]["f32"] - outs[1]["f32"])
+    assert float(d.max()) < 0.25 and float(d.mean()) < 1e-3       # ulp-level coordinate differences x sharp page edges
+    for key in ("u8", "mixed"):
+        d8 = np.abs(outs[0][key].astype(int) - outs[1][key].astype(int))
+        assert int(d8.max()) <= 1 and float((d8 != 0).mean()) < 0.01, key
 
 
 def test_unwarp_properties_and_edges(dev):
