@@ -31,6 +31,13 @@ bool pdl_enabled(int kind) {
   }
   return (mask & kind) != 0;
 }
+// Timing ablation only (results are garbage): DVD_DEBUG_SKIP=<mask> drops every launch of the given kernel kinds, so that the
+// difference in ms/step is the true in-graph cost of that class (ncu durations are cold-cache and serialised).
+bool debug_skip(int kind) {
+  static int mask = -1;
+  if (mask < 0) { const char* m = getenv("DVD_DEBUG_SKIP"); mask = m ? atoi(m) : 0; }
+  return (mask & kind) != 0;
+}
 
 }  // namespace dvd
 

@@ -52,9 +52,11 @@ constexpr int kHeads = 6;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled(int kind = 0xF);     // kind: 1 = GEMM, 2 = attention, 4 = layer norm, 8 = depthwise conv (DVD_PDL_MASK selects)
+bool debug_skip(int kind);            // DVD_DEBUG_SKIP=<mask of kinds>: timing ablation, see api.cu
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  if (debug_skip(kind)) return cudaSuccess;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];

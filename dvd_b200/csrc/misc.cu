@@ -1,4 +1,5 @@
 #include "misc.cuh"
+#include <algorithm>
 
 namespace dvd {
 
@@ -517,55 +518,86 @@ __global__ void __launch_bounds__(256) k_dwconv(const float4* __restrict__ in, c
   float r0 = fmaxf(acc.x * s.x + t.x, 0.f), r1 = fmaxf(acc.y * s.y + t.y, 0.f), r2 = fmaxf(acc.z * s.z + t.z, 0.f), r3 = fmaxf(acc.w * s.w + t.w, 0.f);
   store4(out, out16, i * 4, r0, r1, r2, r3);
 }
-// bf16 in / bf16 out variant for the tensor path: 8 channels (16 bytes) per thread, fp32 accumulation
+// bf16 in / bf16 out variant for the tensor path: 8 channels (16 bytes) per thread, fp32 accumulation.
+// CTA = 8 x-positions (one per warp) x 256 channels (8 per lane) x a vertical strip of RS output rows.  The 9 x 256 tap weights and
+// the BN scale / shift of the CTA's channels are staged once in shared memory (they do not depend on the previous kernel, so this runs
+// ahead of griddepcontrol.wait); a thread walks the strip column by column (kx outer): 3 weight rows (ky) in registers, every input
+// row of the strip loaded once and fed to up to three output rows -> (RS+2)*3 activation loads + 18 LDS.128 per RS outputs, ~80
+// registers, one wave of 512 CTAs.
+template <int RS>
 __global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ sc,
-                                                     const float* __restrict__ sh, uint4* __restrict__ out, int C8, size_t total) {
+                                                     const float* __restrict__ sh, uint4* __restrict__ out, int C8) {
+  __shared__ __align__(16) float s_w[9][256];
+  __shared__ __align__(16) float s_sc[256], s_sh[256];
   pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c8 = blockIdx.x * 32 + lane;                  // 8-channel group of this thread
+  const int x = blockIdx.y * 8 + warp;
+  const int strips = 32 / RS;
+  const size_t n = blockIdx.z / strips;
+  const int y0 = (blockIdx.z % strips) * RS;
+  const int C = C8 * 8, cb = blockIdx.x * 256;            // first channel of the CTA
+  for (int e = threadIdx.x; e < 9 * 256; e += 256) s_w[e >> 8][e & 255] = (cb + (e & 255) < C) ? __ldg(w9 + (size_t)(e >> 8) * C + cb + (e & 255)) : 0.f;
+  s_sc[threadIdx.x] = (cb + threadIdx.x < C) ? __ldg(sc + cb + threadIdx.x) : 0.f;
+  s_sh[threadIdx.x] = (cb + threadIdx.x < C) ? __ldg(sh + cb + threadIdx.x) : 0.f;
+  __syncthreads();
   pdl_wait();
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = i % C8; const size_t row = i / C8;
-  const int tok = row % 1024; const size_t n = row / 1024;
-  const int y = tok / 32, x = tok % 32;
-  const int C = C8 * 8;
-  float acc[8];
+  if (c8 >= C8) return;
+  float acc[RS][8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int o = 0; o < RS; ++o)
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int yy = y + ky - 1;
-    if (yy < 0 || yy >= 32) continue;
+    for (int k = 0; k < 8; ++k) acc[o][k] = 0.f;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int xx = x + kx - 1;
-      if (xx < 0 || xx >= 32) continue;
-      const uint4 v = __ldg(in + (n * 1024 + yy * 32 + xx) * C8 + c);
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)(ky * 3 + kx) * C + c * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)(ky * 3 + kx) * C + c * 8 + 4));
+  for (int kx = 0; kx < 3; ++kx) {
+    const int xx = x + kx - 1;
+    if (xx < 0 || xx >= 32) continue;
+    float w[3][8];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][lane * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][lane * 8 + 4]);
+      w[ky][0] = w0.x; w[ky][1] = w0.y; w[ky][2] = w0.z; w[ky][3] = w0.w; w[ky][4] = w1.x; w[ky][5] = w1.y; w[ky][6] = w1.z; w[ky][7] = w1.w;
+    }
+#pragma unroll
+    for (int r = -1; r <= RS; ++r) {
+      const int yy = y0 + r;
+      if (yy < 0 || yy >= 32) continue;
+      const uint4 v = __ldg(in + (n * 1024 + yy * 32 + xx) * C8 + c8);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-      acc[0] = fmaf(__low2float(h[0]), w0.x, acc[0]); acc[1] = fmaf(__high2float(h[0]), w0.y, acc[1]);
-      acc[2] = fmaf(__low2float(h[1]), w0.z, acc[2]); acc[3] = fmaf(__high2float(h[1]), w0.w, acc[3]);
-      acc[4] = fmaf(__low2float(h[2]), w1.x, acc[4]); acc[5] = fmaf(__high2float(h[2]), w1.y, acc[5]);
-      acc[6] = fmaf(__low2float(h[3]), w1.z, acc[6]); acc[7] = fmaf(__high2float(h[3]), w1.w, acc[7]);
+      const float f[8] = {__low2float(h[0]), __high2float(h[0]), __low2float(h[1]), __high2float(h[1]),
+                          __low2float(h[2]), __high2float(h[2]), __low2float(h[3]), __high2float(h[3])};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int o = r + 1 - ky;                          // output row (inside the strip) that sees input row r through tap row ky
+        if (o < 0 || o >= RS) continue;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[o][k] = fmaf(f[k], w[ky][k], acc[o][k]);
+      }
     }
   }
-  const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c * 8)), s1 = __ldg(reinterpret_cast<const float4*>(sc + c * 8 + 4));
-  const float4 t0 = __ldg(reinterpret_cast<const float4*>(sh + c * 8)), t1 = __ldg(reinterpret_cast<const float4*>(sh + c * 8 + 4));
-  const float r[8] = {fmaxf(acc[0] * s0.x + t0.x, 0.f), fmaxf(acc[1] * s0.y + t0.y, 0.f), fmaxf(acc[2] * s0.z + t0.z, 0.f),
-                      fmaxf(acc[3] * s0.w + t0.w, 0.f), fmaxf(acc[4] * s1.x + t1.x, 0.f), fmaxf(acc[5] * s1.y + t1.y, 0.f),
-                      fmaxf(acc[6] * s1.z + t1.z, 0.f), fmaxf(acc[7] * s1.w + t1.w, 0.f)};
-  uint4 o;
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(r[0], r[1]), p1 = __floats2bfloat162_rn(r[2], r[3]);
-  __nv_bfloat162 p2 = __floats2bfloat162_rn(r[4], r[5]), p3 = __floats2bfloat162_rn(r[6], r[7]);
-  o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-  o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-  out[i] = o;
+  const float4 s0 = *reinterpret_cast<const float4*>(&s_sc[lane * 8]), s1 = *reinterpret_cast<const float4*>(&s_sc[lane * 8 + 4]);
+  const float4 t0 = *reinterpret_cast<const float4*>(&s_sh[lane * 8]), t1 = *reinterpret_cast<const float4*>(&s_sh[lane * 8 + 4]);
+#pragma unroll
+  for (int o = 0; o < RS; ++o) {
+    const float r8[8] = {fmaxf(acc[o][0] * s0.x + t0.x, 0.f), fmaxf(acc[o][1] * s0.y + t0.y, 0.f), fmaxf(acc[o][2] * s0.z + t0.z, 0.f),
+                         fmaxf(acc[o][3] * s0.w + t0.w, 0.f), fmaxf(acc[o][4] * s1.x + t1.x, 0.f), fmaxf(acc[o][5] * s1.y + t1.y, 0.f),
+                         fmaxf(acc[o][6] * s1.z + t1.z, 0.f), fmaxf(acc[o][7] * s1.w + t1.w, 0.f)};
+    uint4 ov;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(r8[0], r8[1]), p1 = __floats2bfloat162_rn(r8[2], r8[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(r8[4], r8[5]), p3 = __floats2bfloat162_rn(r8[6], r8[7]);
+    ov.x = *reinterpret_cast<uint32_t*>(&p0); ov.y = *reinterpret_cast<uint32_t*>(&p1);
+    ov.z = *reinterpret_cast<uint32_t*>(&p2); ov.w = *reinterpret_cast<uint32_t*>(&p3);
+    out[(n * 1024 + (size_t)(y0 + o) * 32 + x) * C8 + c8] = ov;
+  }
 }
 int dwconv3x3_bn_relu_bf16(const __nv_bfloat16* in, const float* w9c, const float* scale, const float* shift, __nv_bfloat16* out, int N, int C,
                            cudaStream_t st) {
   DVD_REQUIRE(in && w9c && scale && shift && out && C % 8 == 0, "dwconv_bf16: bad args");
-  size_t total = (size_t)N * 1024 * (C / 8);
-  DVD_CUDA(launch_pdl(8, k_dwconv_bf16, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, (const uint4*)in, w9c, scale, shift, (uint4*)out, C / 8, total));
+  constexpr int RS = 4;
+  DVD_REQUIRE((long long)N * (32 / RS) <= 65535, "dwconv_bf16: batch too large for the grid");
+  DVD_CUDA(launch_pdl(8, k_dwconv_bf16<RS>, dim3(cdiv(C / 8, 32), 4, N * (32 / RS)), dim3(256), (size_t)0, st, (const uint4*)in, w9c, scale, shift,
+                      (uint4*)out, C / 8));
   DVD_LAUNCH_CHECK("k_dwconv_bf16");
   return 0;
 }
