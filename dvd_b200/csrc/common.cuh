@@ -66,6 +66,22 @@ inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// Same, for a kernel launched as thread-block clusters of (clx, cly, 1) CTAs.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_cluster(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int clx, int cly,
+                                      Args... args) {
+  if (debug_skip(kind)) return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled(kind) ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = clx; attr[1].val.clusterDim.y = cly; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

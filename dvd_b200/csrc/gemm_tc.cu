@@ -11,6 +11,7 @@
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace dvd {
 
@@ -87,6 +88,24 @@ int make_tmap_image3d(CUtensorMap* out, const void* base, int elem_bytes, uint64
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------- cluster helpers (TMA multicast variant)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one TMA box fetched from L2 ONCE and written to the same shared-memory offset of every CTA in `mask` (each destination's mbarrier
+// at the same offset receives the transaction bytes)
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+               : "memory");
+}
+// arrive (once all previously issued MMAs of this CTA have completed) on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------- kernel
 constexpr int TBM = 128, TBK = 64;
 
@@ -106,11 +125,18 @@ struct TcCfg {
 
 struct ConvGeom { int H, W, Cin; };      // CONV: A is an NHWC activation, K = 9 * Cin ordered [ky][kx][Cin]
 
-template <int BN, bool CONV>
+// CLN x CLM > 1: the CTAs of a (CLN, CLM, 1) cluster share operand tiles through TMA multicast.  The CLN CTAs of a cluster row work on
+// the same 128 rows of A, the CLM CTAs of a cluster column on the same BN rows of W: every CTA fetches 1/CLN of the A tile and 1/CLM of
+// the W tile and multicasts them, so the L2 -> SM traffic of the main loop (what bounds the 128x128 kernel: ~64 FLOP per loaded byte)
+// drops by CLN resp. CLM.  A stage may be refilled once every CTA that receives data from this one has consumed it, so the MMA
+// issuer's commit arrives on the `empty` barrier of all CTAs of its cluster row and column (CLN + CLM - 1 arrivals per phase).
+template <int BN, bool CONV, int CLN = 1, int CLM = 1>
 __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                  int M, int N, int K, Epilogue e, ConvGeom cg) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int CL = CLN * CLM;
+  static_assert(!CONV || CL == 1, "the implicit-GEMM conv path is not clustered");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES);
@@ -125,7 +151,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
   pdl_trigger();                                        // the next kernel of the stream may start its own prologue
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CLN + CLM - 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -133,8 +159,17 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                       // peers' barriers are initialised before anything is multicast to them
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // position in the cluster: rank = x + y * CLN (grid dims are multiples of the cluster dims, checked on the host)
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  const int cxp = crank % CLN, cyp = crank / CLN;
+  uint16_t mask_row = 0, mask_col = 0;                  // CTAs sharing my A tile / my W tile
+#pragma unroll
+  for (int i = 0; i < CLN; ++i) mask_row |= (uint16_t)(1u << (cyp * CLN + i));
+#pragma unroll
+  for (int i = 0; i < CLM; ++i) mask_col |= (uint16_t)(1u << (i * CLN + cxp));
   pdl_wait();                                           // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
@@ -151,14 +186,24 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
         mbar_wait(&empty[s], (it & 1) ^ 1);
         uint8_t* a = smem + s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        if (CONV) {
-          const int tap = kb / cblocks, cb = kb % cblocks;
-          tma_load_4d(a, &tmA, &full[s], cb * 64, cx + tap % 3 - 1, cy + tap / 3 - 1, cn);
+        if (CL > 1) {
+          // my slice of the A tile (rows cxp * 128/CLN ...) to the cluster row, my slice of the W tile to the cluster column;
+          // the tensor-map boxes are 128/CLN and min(128, BN/CLM) rows tall
+          constexpr int AR = TBM / CLN, BR = BN / CLM, BBOX = BR > 128 ? 128 : BR;
+          tma_load_2d_mc(a + cxp * AR * TBK * 2, &tmA, &full[s], kb * TBK, m0 + cxp * AR, mask_row);
+#pragma unroll
+          for (int j = 0; j < BR / BBOX; ++j)
+            tma_load_2d_mc(a + Cfg::A_BYTES + (cyp * BR + j * BBOX) * TBK * 2, &tmB, &full[s], kb * TBK, n0 + cyp * BR + j * BBOX, mask_col);
         } else {
-          tma_load_2d(a, &tmA, &full[s], kb * TBK, m0);
+          if (CONV) {
+            const int tap = kb / cblocks, cb = kb % cblocks;
+            tma_load_4d(a, &tmA, &full[s], cb * 64, cx + tap % 3 - 1, cy + tap / 3 - 1, cn);
+          } else {
+            tma_load_2d(a, &tmA, &full[s], kb * TBK, m0);
+          }
+          tma_load_2d(a + Cfg::A_BYTES, &tmB, &full[s], kb * TBK, n0);
+          if (BN == 256) tma_load_2d(a + Cfg::A_BYTES + 128 * TBK * 2, &tmB, &full[s], kb * TBK, n0 + 128);
         }
-        tma_load_2d(a + Cfg::A_BYTES, &tmB, &full[s], kb * TBK, n0);
-        if (BN == 256) tma_load_2d(a + Cfg::A_BYTES + 128 * TBK * 2, &tmB, &full[s], kb * TBK, n0 + 128);
       }
     }
     __syncwarp();
@@ -176,7 +221,8 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
           // advancing K inside the 128-byte swizzle atom = +32 bytes on the start address
           mma_f16_ss(tmem_base, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
         }
-        mma_commit(&empty[s]);                           // stage reusable once these MMAs have read it
+        if (CL > 1) mma_commit_mc(&empty[s], mask_row | mask_col);   // every CTA that sends me operands learns the stage is free
+        else        mma_commit(&empty[s]);               // stage reusable once these MMAs have read it
       }
       mma_commit(tmem_full);                             // accumulator complete
     }
@@ -275,6 +321,21 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (CL > 1) cluster_sync_all();                       // peers may still be arriving on my `empty` barriers
+}
+
+template <int BN, int CLN, int CLM>
+static int launch_tc_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epilogue& e, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DVD_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, false, CLN, CLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(N, BN), cdiv(M, TBM));
+  ConvGeom cg{0, 0, 0};
+  DVD_CUDA(launch_pdl_cluster(1, k_gemm_tc<BN, false, CLN, CLM>, grid, dim3(128), (size_t)TcCfg<BN>::SMEM, st, CLN, CLM, tmA, tmB, M, N, K, e, cg));
+  DVD_LAUNCH_CHECK("k_gemm_tc (cluster)");
+  return 0;
 }
 
 template <int BN, bool CONV>
@@ -345,6 +406,34 @@ int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ld
   bool bn96 = false;
   if (const char* f = getenv("DVD_GEMM_BN")) bn96 = (atoi(f) == 96) && !wide && !narrow && N % 96 == 0;
   CUtensorMap tmA, tmB;
+  // TMA-multicast clusters (experiment, OFF by default): DVD_GEMM_CLUSTER=22 / 12 / 21 shares the A tile along N and / or the W tile
+  // along M inside (2,2) / (1,2) / (2,1) clusters.  Measured on B200 (tools/gemm_bench.py): correct, but 5-10% SLOWER than independent
+  // CTAs on every denoiser shape (e.g. 2048x1536x1536: 25.6 vs 23.6 us; 16384x4608x1536: 292 vs 235 us) - halving the L2 reads does not
+  // help because the main loop is bound by what each SM can take in, and the cluster couples the progress of its CTAs.
+  if (!narrow && !bn96) {
+    static const int cl_env = getenv("DVD_GEMM_CLUSTER") ? atoi(getenv("DVD_GEMM_CLUSTER")) : 0;
+    const int bn = wide ? 256 : 128;
+    const int gx = N / bn, gy = M / 128;
+    int cl = 0;
+    if (N % bn == 0 && cl_env != 0) {
+      if (gx % 2 == 0 && gy % 2 == 0) cl = 22; else if (gy % 2 == 0) cl = 12; else if (gx % 2 == 0) cl = 21;
+      if (cl_env == 12 && gy % 2 == 0) cl = 12;
+      if (cl_env == 21 && gx % 2 == 0) cl = 21;
+    }
+    if (cl) {
+      const int cln = cl / 10, clm = cl % 10;
+      rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128 / cln, 64); if (rc) return rc;
+      rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, std::min(128, bn / clm), 64); if (rc) return rc;
+      if (wide) {
+        if (cl == 22) return launch_tc_cluster<256, 2, 2>(tmA, tmB, M, N, K, e, st);
+        if (cl == 12) return launch_tc_cluster<256, 1, 2>(tmA, tmB, M, N, K, e, st);
+        return launch_tc_cluster<256, 2, 1>(tmA, tmB, M, N, K, e, st);
+      }
+      if (cl == 22) return launch_tc_cluster<128, 2, 2>(tmA, tmB, M, N, K, e, st);
+      if (cl == 12) return launch_tc_cluster<128, 1, 2>(tmA, tmB, M, N, K, e, st);
+      return launch_tc_cluster<128, 2, 1>(tmA, tmB, M, N, K, e, st);
+    }
+  }
   rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64); if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, narrow ? 64 : (bn96 ? 96 : 128), 64); if (rc) return rc;
   ConvGeom cg{0, 0, 0};

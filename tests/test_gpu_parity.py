@@ -360,10 +360,12 @@ def test_end_to_end_dewarp_psnr(dev, models, golden_dir):
 
 
 # ----------------------------------------------------------------------------------------------- kernel variants and the evaluation drop-in
-@pytest.mark.parametrize("env", [{"DVD_GEMM_V1": "1"}, {"DVD_GEMM_V2": "1"}, {"DVD_GEMM_V3": "1"}])
+@pytest.mark.parametrize("env", [{"DVD_GEMM_V1": "1"}, {"DVD_GEMM_V2": "1"}, {"DVD_GEMM_V3": "1"}, {"DVD_GEMM_V1": "1", "DVD_GEMM_CLUSTER": "22"},
+                                 {"DVD_GEMM_V1": "1", "DVD_GEMM_CLUSTER": "12"}, {"DVD_GEMM_V1": "1", "DVD_GEMM_CLUSTER": "21"}])
 def test_gemm_kernel_variants_agree(dev, env):
-    """The three tcgen05 GEMM kernels (two CTAs/SM, persistent double-buffered, CTA-pair cta_group::2) are selected by shape at
-    run time; force each one (env is read once per process, hence the subprocess) over the denoiser's shapes."""
+    """The tcgen05 GEMM kernels (two CTAs/SM with or without TMA-multicast clusters of shape 2x2 / 1x2 / 2x1, persistent
+    double-buffered, CTA-pair cta_group::2) are selected by shape at run time; force each one (env is read once per process, hence
+    the subprocess) over the denoiser's shapes."""
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "gemm_bench.py")], env={**os.environ, **env}, capture_output=True,
