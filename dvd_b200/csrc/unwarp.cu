@@ -479,29 +479,60 @@ __device__ __forceinline__ void tap_setup(const TileTab& tb, int k, float lx0, f
   wnw = bxw * byw; wne = ax * byw; wsw = bxw * ay; wse = ax * ay;
 }
 
+// One pixel gathered from global memory (pixels whose taps fall outside the staged window).  Same accumulation order as the staged path.
 template <int IN_U8, int C>
-__device__ __forceinline__ float gather_tap4(const void* __restrict__ photo_, int b, int c, int H, int W, int x0, int y0, float wnw, float wne,
-                                             float wsw, float wse) {
-  // per-tap validity (zeros padding) tested before any address is formed; same accumulation order as the staged path
+__device__ __forceinline__ void gather_px(const void* __restrict__ photo_, int b, int H, int W, int x0, int y0, float wnw, float wne,
+                                          float wsw, float wse, float (&res)[C]) {
+  const long long plane = (long long)H * W;
+  if (((unsigned)x0 < (unsigned)(W - 1)) & ((unsigned)y0 < (unsigned)(H - 1))) {
+    // all four taps inside the photo: one base address, no predicates
+    if (IN_U8) {
+      const uint8_t* q = (const uint8_t*)photo_ + ((size_t)b * plane + (size_t)y0 * W + x0) * C;
+      const uint8_t* q1 = q + (size_t)W * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float v = (float)__ldg(q + c) * wnw;
+        v += (float)__ldg(q + C + c) * wne;
+        v += (float)__ldg(q1 + c) * wsw;
+        v += (float)__ldg(q1 + C + c) * wse;
+        res[c] = v;
+      }
+    } else {
+      const float* q = (const float*)photo_ + (size_t)b * C * plane + (size_t)y0 * W + x0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float* a = q + (size_t)c * plane;
+        float v = __ldg(a) * wnw;
+        v += __ldg(a + 1) * wne;
+        v += __ldg(a + W) * wsw;
+        v += __ldg(a + W + 1) * wse;
+        res[c] = v;
+      }
+    }
+    return;
+  }
+  // per-tap validity (zeros padding) tested before any address is formed
   const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 >= -1 && x0 < W - 1;
   const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 >= -1 && y0 < H - 1;
-  const long long plane = (long long)H * W;
-  float v = 0.f;
-  if (IN_U8) {
-    const uint8_t* base = (const uint8_t*)photo_ + (size_t)b * plane * C + c;
-    v = (vy0 && vx0 ? (float)__ldg(base + ((long long)y0 * W + x0) * C) : 0.f) * wnw;
-    v += (vy0 && vx1 ? (float)__ldg(base + ((long long)y0 * W + x0 + 1) * C) : 0.f) * wne;
-    v += (vy1 && vx0 ? (float)__ldg(base + ((long long)(y0 + 1) * W + x0) * C) : 0.f) * wsw;
-    v += (vy1 && vx1 ? (float)__ldg(base + ((long long)(y0 + 1) * W + x0 + 1) * C) : 0.f) * wse;
-  } else {
-    const float* base = (const float*)photo_ + ((size_t)b * C + c) * plane;
-    v = (vy0 && vx0 ? __ldg(base + (long long)y0 * W + x0) : 0.f) * wnw;
-    v += (vy0 && vx1 ? __ldg(base + (long long)y0 * W + x0 + 1) : 0.f) * wne;
-    v += (vy1 && vx0 ? __ldg(base + (long long)(y0 + 1) * W + x0) : 0.f) * wsw;
-    v += (vy1 && vx1 ? __ldg(base + (long long)(y0 + 1) * W + x0 + 1) : 0.f) * wse;
+  const bool any = (vx0 | vx1) && (vy0 | vy1);      // a pixel with no valid tap is exactly 0 even when its (wild) weights are inf / nan
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float v = 0.f;
+    if (IN_U8) {
+      const uint8_t* base = (const uint8_t*)photo_ + (size_t)b * plane * C + c;
+      v = (vy0 && vx0 ? (float)__ldg(base + ((long long)y0 * W + x0) * C) : 0.f) * wnw;
+      v += (vy0 && vx1 ? (float)__ldg(base + ((long long)y0 * W + x0 + 1) * C) : 0.f) * wne;
+      v += (vy1 && vx0 ? (float)__ldg(base + ((long long)(y0 + 1) * W + x0) * C) : 0.f) * wsw;
+      v += (vy1 && vx1 ? (float)__ldg(base + ((long long)(y0 + 1) * W + x0 + 1) * C) : 0.f) * wse;
+    } else {
+      const float* base = (const float*)photo_ + ((size_t)b * C + c) * plane;
+      v = (vy0 && vx0 ? __ldg(base + (long long)y0 * W + x0) : 0.f) * wnw;
+      v += (vy0 && vx1 ? __ldg(base + (long long)y0 * W + x0 + 1) : 0.f) * wne;
+      v += (vy1 && vx0 ? __ldg(base + (long long)(y0 + 1) * W + x0) : 0.f) * wsw;
+      v += (vy1 && vx1 ? __ldg(base + (long long)(y0 + 1) * W + x0 + 1) : 0.f) * wse;
+    }
+    res[c] = any ? v : 0.f;
   }
-  // a pixel with no valid tap is exactly 0 even when its (wild) weights are inf / nan
-  return (vx0 | vx1) && (vy0 | vy1) ? v : 0.f;
 }
 
 // The four coarse-map values behind one entry (tile row rr8, window column kk) of a tile's blended map window + the vertical weight.
@@ -567,7 +598,7 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) k_unwarp_tma(const __grid_co
       xs = max(min(xs, inner_w & ~15), -ROW);
       const int wy0 = max(min(max(mny, -(1 << 20)) - 1, H), -SB_ROWS);
       const int need = min(mxy, 1 << 20) + 3 - wy0;                        // rows wy0 .. mxy + 2
-      const int nq = max(1, min((need + 7) >> 3, SB_ROWS / 8));
+      const int nq = max(1, min((need + 7) >> 3, SB_ROWS / 8));       // a window that is too small is still loaded: most of its pixels hit it
       tc::mbar_wait(&s_empty[s], ph ^ 1);
       if (lane == 0) {
         s_win[s] = make_int4(xs, wy0, 8 * nq, 0);
@@ -650,7 +681,7 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) k_unwarp_tma(const __grid_co
       tap_setup(tb, k, lx0, lx1, bxv, warp + 8 * p, g.affine, fw, fh, x0, y0, wnw, wne, wsw, wse);
       // all four taps inside the staged window?  (inner elements [xs, xs+ROW), rows [wy0, wy0+nrows))
       const unsigned ux = (IN_U8 ? (unsigned)x0 * (unsigned)C : (unsigned)x0) - (unsigned)xs, uy = (unsigned)y0 - (unsigned)wy0;
-      const bool in = (ux <= (unsigned)(ROW - (IN_U8 ? 2 * C : 2))) & (uy <= (unsigned)(nrows - 2)) &
+      const bool in = (ux <= (unsigned)(ROW - (IN_U8 ? 2 * C : 2))) & (uy < (unsigned)max(nrows - 1, 0)) &
                       (!IN_U8 || (x0 > -(1 << 20) && x0 < (1 << 20)));               // x0 * C must not have wrapped
       float res[C];
       if (__all_sync(0xffffffffu, in) || in) {
@@ -676,8 +707,7 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) k_unwarp_tma(const __grid_co
           }
         }
       } else {
-#pragma unroll
-        for (int c = 0; c < C; ++c) res[c] = gather_tap4<IN_U8, C>(photo_, cb, c, H, W, x0, y0, wnw, wne, wsw, wse);
+        gather_px<IN_U8, C>(photo_, cb, H, W, x0, y0, wnw, wne, wsw, wse, res);
       }
       if (OUT_U8) {
         uint8_t* o = s_out + ((warp + 8 * p) * T2 + lane) * C;
