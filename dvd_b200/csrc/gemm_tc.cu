@@ -106,8 +106,18 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------- optional phase trace (-DDVD_GEMM_TRACE)
+#ifdef DVD_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[2048][8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define DVD_TRACE(slot) do { g_gemm_trace[(blockIdx.y * gridDim.x + blockIdx.x) & 2047][slot] = gtime(); } while (0)
+#else
+#define DVD_TRACE(slot) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------- kernel
 constexpr int TBM = 128, TBK = 64;
+constexpr int TC_THREADS = 256;          // warp 0: TMA producer, warp 1: MMA issuer, all 8 warps: epilogue
 
 template <int BN>
 struct TcCfg {
@@ -117,7 +127,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CW = BN < 128 ? BN : 128;                          // columns per epilogue pass
   static constexpr int STAGE_LD = CW + 4;                                 // fp32 staging row stride (16-byte aligned, conflict-free)
-  static constexpr int STAGING_BYTES = 4 * 32 * STAGE_LD * 4;             // 4 warps x 32 rows
+  static constexpr int STAGING_BYTES = 4 * 32 * STAGE_LD * 4;             // 4 row groups x 32 rows
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static_assert(STAGING_BYTES <= RING_BYTES, "epilogue staging must fit in the (drained) operand ring");
   static constexpr int SMEM = RING_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
@@ -131,7 +141,7 @@ struct ConvGeom { int H, W, Cin; };      // CONV: A is an NHWC activation, K = 9
 // drops by CLN resp. CLM.  A stage may be refilled once every CTA that receives data from this one has consumed it, so the MMA
 // issuer's commit arrives on the `empty` barrier of all CTAs of its cluster row and column (CLN + CLM - 1 arrivals per phase).
 template <int BN, bool CONV, int CLN = 1, int CLM = 1>
-__global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                  int M, int N, int K, Epilogue e, ConvGeom cg) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -150,6 +160,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
 
   pdl_trigger();                                        // the next kernel of the stream may start its own prologue
   if (threadIdx.x == 0) {
+    DVD_TRACE(0);                                       // CTA start
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CLN + CLM - 1); }
     mbar_init(tmem_full, 1);
@@ -171,6 +182,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
 #pragma unroll
   for (int i = 0; i < CLM; ++i) mask_col |= (uint16_t)(1u << (i * CLN + cxp));
   pdl_wait();                                           // everything above overlapped the previous kernel's tail
+  if (threadIdx.x == 0) DVD_TRACE(1);                   // prologue done, predecessor finished
 
   if (warp == 0) {
     if (lane == 0) {
@@ -214,6 +226,8 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES, it = kb / STAGES;
         mbar_wait(&full[s], it & 1);
+        if (kb == 0) DVD_TRACE(2);                      // first stage landed
+        if (kb == nkb - 1) DVD_TRACE(3);                // last stage landed
         fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES), b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
@@ -230,20 +244,27 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
   }
 
   // ===== epilogue.  tmem_full => every MMA has retired, so every TMA write has been consumed: the operand ring is dead
-  // and is reused as an fp32 staging tile.  Phase 1 (thread = row, TMEM lane): TMEM -> registers -> staging (+ the
-  // transposed V^T store, which is naturally coalesced in this mapping).  Phase 2 (lane = 4 consecutive columns):
-  // staging -> fused epilogue -> fully coalesced 512-byte row segments in global memory.
+  // and is reused as an fp32 staging tile.  The epilogue is a third of a batch-1 launch (tools/gemm_trace.py), so all 8 warps take
+  // part: warps w and w+4 own the same 32 rows (a warp can only read the TMEM lanes 32*(w%4)..+31) and split the columns in
+  // phase 1 and the rows in phase 2, synchronised by a 64-thread named barrier per row group.
+  //   Phase 1 (thread = row, TMEM lane): TMEM -> registers -> staging (+ the transposed V^T store, which is naturally
+  //   coalesced in this mapping).  Phase 2 (lane = 4 consecutive columns): staging -> fused epilogue -> fully coalesced
+  //   512-byte row segments in global memory.
   mbar_wait(tmem_full, 0);
+  if (threadIdx.x == 0) DVD_TRACE(4);                   // accumulator complete
   fence_after_sync();
   constexpr int CW = Cfg::CW, SLD = Cfg::STAGE_LD;
-  float* stage = reinterpret_cast<float*>(smem) + warp * 32 * SLD;
-  const int row_t = m0 + warp * 32 + lane;               // phase-1 row of this thread (M % 128 == 0 is checked on the host)
+  static_assert((CW / 2) % 32 == 0, "each half of an epilogue pass is a whole number of 32-column TMEM loads");
+  const int wq = warp & 3, wh = warp >> 2;               // row group (TMEM lane quarter), column / row half
+  float* stage = reinterpret_cast<float*>(smem) + wq * 32 * SLD;
+  const int row_t = m0 + wq * 32 + lane;                 // phase-1 row of this thread (M % 128 == 0 is checked on the host)
+  auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory"); };
 #pragma unroll 1
   for (int pass = 0; pass < BN / CW; ++pass) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < CW; c0 += 32) {
+    for (int c0 = wh * (CW / 2); c0 < (wh + 1) * (CW / 2); c0 += 32) {
       uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pass * CW + c0), r);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(pass * CW + c0), r);
       tmem_ld_wait();
       float* srow = stage + lane * SLD + c0;
 #pragma unroll
@@ -263,8 +284,8 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
         for (int j = 0; j < 32; ++j) o[(size_t)j * 1024] = __float2bfloat16_rn(__uint_as_float(r[j]) + bv[j]);
       }
     }
-    __syncwarp();
-    // ---- phase 2
+    pair_sync();                                         // both column halves of the row group are staged
+    // ---- phase 2: this warp finishes rows wh*16 .. wh*16+15 of the group
     const int col = n0 + pass * CW + 4 * lane;
     if (4 * lane < CW && col < N) {
       float4 cb = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f), ct = cb, cgate = cs;
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
       const bool has_scale = e.scale != nullptr, has_gate = e.gate != nullptr;
       const int act = e.act;
 #pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += 8) {
+      for (int r0 = wh * 16; r0 < wh * 16 + 16; r0 += 8) {
         float4 a[8], q[8], p[8];
         // batch the loads of 8 rows (staging, residual, pos-embed) before any dependent math or store
 #pragma unroll
@@ -282,7 +303,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
         if (e.resid) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row = m0 + warp * 32 + r0 + i;
+            const int row = m0 + wq * 32 + r0 + i;
             const int rr = e.resid_mod ? (row % e.resid_mod) : row;
             q[i] = *reinterpret_cast<const float4*>(e.resid + (size_t)rr * e.ldr + col);      // may alias e.out (in-place residual)
           }
@@ -290,13 +311,13 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
         if (e.pos) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row = m0 + warp * 32 + r0 + i;
+            const int row = m0 + wq * 32 + r0 + i;
             p[i] = __ldg(reinterpret_cast<const float4*>(e.pos + (size_t)(row % e.pos_rows) * N + col));
           }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = m0 + warp * 32 + r0 + i;
+          const int row = m0 + wq * 32 + r0 + i;
           float v[4] = {a[i].x + cb.x, a[i].y + cb.y, a[i].z + cb.z, a[i].w + cb.w};
           if (has_scale) { v[0] = v[0] * cs.x + ct.x; v[1] = v[1] * cs.y + ct.y; v[2] = v[2] * cs.z + ct.z; v[3] = v[3] * cs.w + ct.w; }
           if (act == ACT_RELU) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
@@ -316,10 +337,11 @@ __global__ void __launch_bounds__(128) k_gemm_tc(const __grid_constant__ CUtenso
         }
       }
     }
-    __syncwarp();
+    pair_sync();                                         // the staging rows may be overwritten by the next pass
   }
   fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) DVD_TRACE(5);                   // epilogue done
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   if (CL > 1) cluster_sync_all();                       // peers may still be arriving on my `empty` barriers
 }
@@ -333,7 +355,7 @@ static int launch_tc_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, int
   }
   dim3 grid(cdiv(N, BN), cdiv(M, TBM));
   ConvGeom cg{0, 0, 0};
-  DVD_CUDA(launch_pdl_cluster(1, k_gemm_tc<BN, false, CLN, CLM>, grid, dim3(128), (size_t)TcCfg<BN>::SMEM, st, CLN, CLM, tmA, tmB, M, N, K, e, cg));
+  DVD_CUDA(launch_pdl_cluster(1, k_gemm_tc<BN, false, CLN, CLM>, grid, dim3(TC_THREADS), (size_t)TcCfg<BN>::SMEM, st, CLN, CLM, tmA, tmB, M, N, K, e, cg));
   DVD_LAUNCH_CHECK("k_gemm_tc (cluster)");
   return 0;
 }
@@ -346,7 +368,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
     attr_set = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, TBM));
-  DVD_CUDA(launch_pdl(1, k_gemm_tc<BN, CONV>, grid, dim3(128), (size_t)TcCfg<BN>::SMEM, st, tmA, tmB, M, N, K, e, cg));
+  DVD_CUDA(launch_pdl(1, k_gemm_tc<BN, CONV>, grid, dim3(TC_THREADS), (size_t)TcCfg<BN>::SMEM, st, tmA, tmB, M, N, K, e, cg));
   DVD_LAUNCH_CHECK("k_gemm_tc");
   return 0;
 }
@@ -401,16 +423,14 @@ int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ld
   bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) * 100 >= 190LL * kSMs);   // >= ~1.9 SM-fulls of 128x256 tiles (2 CTAs/SM)
   if (const char* f = getenv("DVD_GEMM_WIDE")) wide = (N % 256 == 0) && atoi(f) == 1;     // tuning override
   const bool narrow = (N <= 64);
-  // 128x96 tiles were measured (tools/gemm_bench.py, DVD_GEMM_BN=96): no gain over 128x128 on the N = 1536 shapes (23.5 vs 23.6 us:
-  // those launches are bound by the fixed prologue/epilogue cost, not by SM balance), so they are only reachable for experiments.
-  bool bn96 = false;
-  if (const char* f = getenv("DVD_GEMM_BN")) bn96 = (atoi(f) == 96) && !wide && !narrow && N % 96 == 0;
+  // 128x96 and 128x192 (one CTA per SM, 5-stage ring) tiles were measured on the N = 1536 shapes: no gain over 128x128 (the main loop
+  // already runs at the tensor rate of two co-resident CTAs; the launches are bound by prologue + epilogue, see tools/gemm_trace.py).
   CUtensorMap tmA, tmB;
   // TMA-multicast clusters (experiment, OFF by default): DVD_GEMM_CLUSTER=22 / 12 / 21 shares the A tile along N and / or the W tile
   // along M inside (2,2) / (1,2) / (2,1) clusters.  Measured on B200 (tools/gemm_bench.py): correct, but 5-10% SLOWER than independent
   // CTAs on every denoiser shape (e.g. 2048x1536x1536: 25.6 vs 23.6 us; 16384x4608x1536: 292 vs 235 us) - halving the L2 reads does not
   // help because the main loop is bound by what each SM can take in, and the cluster couples the progress of its CTAs.
-  if (!narrow && !bn96) {
+  if (!narrow) {
     static const int cl_env = getenv("DVD_GEMM_CLUSTER") ? atoi(getenv("DVD_GEMM_CLUSTER")) : 0;
     const int bn = wide ? 256 : 128;
     const int gx = N / bn, gy = M / 128;
@@ -435,9 +455,8 @@ int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ld
     }
   }
   rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64); if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, narrow ? 64 : (bn96 ? 96 : 128), 64); if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, narrow ? 64 : 128, 64); if (rc) return rc;
   ConvGeom cg{0, 0, 0};
-  if (bn96 && !wide) return launch_tc<96, false>(tmA, tmB, M, N, K, e, cg, st);
   if (wide) return launch_tc<256, false>(tmA, tmB, M, N, K, e, cg, st);
   if (narrow) return launch_tc<64, false>(tmA, tmB, M, N, K, e, cg, st);
   return launch_tc<128, false>(tmA, tmB, M, N, K, e, cg, st);
@@ -462,3 +481,9 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* Wt, int B, int
 }
 
 }  // namespace dvd
+
+#ifdef DVD_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int dvd_debug_gemm_trace(unsigned long long* out, int n_ctas) {
+  return (int)cudaMemcpyFromSymbol(out, dvd::g_gemm_trace, (size_t)n_ctas * 8 * sizeof(unsigned long long));
+}
+#endif

@@ -1,6 +1,8 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k unwarp 2>&1 | tail -3
-for amp in 0.05 0.02 0.005; do UW_AMP=$amp timeout 300 python tools/unwarp_bench.py 2>&1 | grep f32; done
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 python bench.py --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], json.dumps(d['roofline_unwarp']['random_init_map']))"
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'])"
+python bench.py --docs 16 --steps 5 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'])"
