@@ -27,7 +27,7 @@ bool pdl_enabled(int kind) {
   if (mask < 0) {
     const char* off = getenv("DVD_NO_PDL");
     const char* m = getenv("DVD_PDL_MASK");
-    mask = (off && off[0] == '1') ? 0 : (m ? atoi(m) : 0xF);
+    mask = (off && off[0] == '1') ? 0 : (m ? atoi(m) : 0x1F);
   }
   return (mask & kind) != 0;
 }

@@ -51,7 +51,7 @@ constexpr int kHeads = 6;
 // fall back to plain stream serialisation.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled(int kind = 0xF);     // kind: 1 = GEMM, 2 = attention, 4 = layer norm, 8 = depthwise conv (DVD_PDL_MASK selects)
+bool pdl_enabled(int kind = 0x1F);    // kind: 1 = GEMM, 2 = attention, 4 = layer norm, 8 = depthwise conv, 16 = small dense layers (DVD_PDL_MASK)
 bool debug_skip(int kind);            // DVD_DEBUG_SKIP=<mask of kinds>: timing ablation, see api.cu
 
 template <typename... KArgs, typename... Args>

@@ -313,10 +313,9 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     float* mean = s.pe; float* hs1 = s.pe + (size_t)N * 1536 * 33; float* hs = hs1 + (size_t)N * 1536;
     float* ws1 = hs + (size_t)N * 1536; float* wsv = ws1 + (size_t)N * 1536;
     DVD_TRY(token_mean(s.X, mean, N, 1536, st));
-    DVD_TRY(gemv(mean, 1536, w.h_scale0.f32, w.h_scale0_b, hs1, 1536, N, 1536, 1536, 0, 0, 1, st));
-    DVD_TRY(gemv(hs1, 1536, w.h_scale2.f32, w.h_scale2_b, hs, 1536, N, 1536, 1536, 0, 0, 3, st));
-    DVD_TRY(gemv(mean, 1536, w.w_scale0.f32, w.w_scale0_b, ws1, 1536, N, 1536, 1536, 0, 0, 1, st));
-    DVD_TRY(gemv(ws1, 1536, w.w_scale2.f32, w.w_scale2_b, wsv, 1536, N, 1536, 1536, 0, 0, 3, st));
+    // h- and w-branch side by side: conv1x1 + ReLU, then conv1x1 + sigmoid (CA:143-157)
+    DVD_TRY(gemv_pair(mean, mean, 1536, w.h_scale0.f32, w.w_scale0.f32, w.h_scale0_b, w.w_scale0_b, hs1, ws1, 1536, N, 1536, 1536, 1, st));
+    DVD_TRY(gemv_pair(hs1, ws1, 1536, w.h_scale2.f32, w.w_scale2.f32, w.h_scale2_b, w.w_scale2_b, hs, wsv, 1536, N, 1536, 1536, 3, st));
     DVD_TRY(posenc_add(s.X, hs, wsv, w.dec_hpe, w.dec_wpe, N, 1536, st));
   }
   // ---- 6 decoder layers (CA:377-396)

@@ -358,32 +358,42 @@ int softmax_rows(float* S, long long rows, int n, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------ small dense layers
 constexpr int GEMV_MAXR = 8;
-// block = 8 warps = 8 output features; the (activated) input rows are staged once per block in shared memory, each warp
-// streams its weight row with 128-bit loads (4 independent loads in flight per lane).
-__global__ void __launch_bounds__(256) k_gemv(const float* __restrict__ in, int ldin, const float* __restrict__ W,
-                                              const float* __restrict__ b, float* __restrict__ out, int ldo, int rows, int N,
-                                              int K, int silu_in, int in_mod, int act) {
+// block = 8 warps = 8 output features.  Each warp first requests its whole weight row (<= 12 x 16 bytes per lane for K <= 1536): the
+// weights do not depend on the previous kernel, so under programmatic dependent launch this HBM fetch (9.4 MB for the 1536x1536
+// layers of the adaptive positional encoding) overlaps the predecessor's execution; only then does the block wait for its input
+// rows, stage them (activated) in shared memory and reduce.
+// blockIdx.y selects one of up to two independent problems of the same shape (the h- and w-branch of the adaptive positional
+// encoding run side by side: two dependent launches per step instead of four).
+struct GemvProb { const float* in[2]; const float* W[2]; const float* b[2]; float* out[2]; };
+__global__ void __launch_bounds__(256) k_gemv(const GemvProb pr, int ldin, int ldo, int rows, int N, int K, int silu_in, int in_mod, int act) {
   extern __shared__ float xs[];                      // [rows][K]
+  const float* __restrict__ in = pr.in[blockIdx.y];
+  const float* __restrict__ W = pr.W[blockIdx.y];
+  const float* __restrict__ b = pr.b[blockIdx.y];
+  float* __restrict__ out = pr.out[blockIdx.y];
+  pdl_trigger();
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int K4 = K >> 2;
+  float4 wv[12];
+  {
+    const float4* wr = reinterpret_cast<const float4*>(W + (size_t)min(j, N - 1) * K);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const int k = lane + 32 * i;
+      wv[i] = (k < K4) ? __ldg(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  pdl_wait();                                        // the input rows are the previous kernel's output
   for (int i = threadIdx.x; i < rows * K; i += 256) {
     const int r = i / K, k = i - r * K;
     float x = __ldg(in + (size_t)r * ldin + (in_mod > 0 ? (k % in_mod) : k));
     xs[i] = silu_in ? silu(x) : x;
   }
   __syncthreads();
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= N) return;
   float acc[GEMV_MAXR];
 #pragma unroll
   for (int r = 0; r < GEMV_MAXR; ++r) acc[r] = 0.f;
-  const float4* wr = reinterpret_cast<const float4*>(W + (size_t)j * K);
-  const int K4 = K >> 2;
-  // the whole weight row of this output (<= 12 x 16 bytes per lane for K <= 1536) is requested before any use
-  float4 wv[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    const int k = lane + 32 * i;
-    wv[i] = (k < K4) ? __ldg(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
     const int k = lane + 32 * i;
@@ -411,17 +421,31 @@ __global__ void __launch_bounds__(256) k_gemv(const float* __restrict__ in, int 
     }
   }
 }
+static int gemv_launch(const GemvProb& pr, int nprob, int ldin, int ldo, int rows, int N, int K, int silu_in, int in_mod, int act, cudaStream_t st) {
+  for (int r0 = 0; r0 < rows; r0 += GEMV_MAXR) {
+    int nr = rows - r0 < GEMV_MAXR ? rows - r0 : GEMV_MAXR;
+    GemvProb q = pr;
+    for (int i = 0; i < nprob; ++i) { q.in[i] = pr.in[i] + (size_t)r0 * ldin; q.out[i] = pr.out[i] + (size_t)r0 * ldo; }
+    DVD_CUDA(launch_pdl(16, k_gemv, dim3(cdiv(N, 8), nprob), dim3(256), (size_t)nr * K * sizeof(float), st, q, ldin, ldo, nr, N, K, silu_in, in_mod,
+                        act));
+    DVD_LAUNCH_CHECK("k_gemv");
+  }
+  return 0;
+}
 int gemv(const float* in, int ldin, const float* W, const float* b, float* out, int ldo, int rows, int N, int K, int silu_in,
          int in_mod, int act, cudaStream_t st) {
   DVD_REQUIRE(in && W && out && N > 0 && K > 0 && K % 4 == 0 && K <= 1536, "gemv: bad args (K=%d)", K);
   DVD_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemv: W must be 16-byte aligned");
-  for (int r0 = 0; r0 < rows; r0 += GEMV_MAXR) {
-    int nr = rows - r0 < GEMV_MAXR ? rows - r0 : GEMV_MAXR;
-    k_gemv<<<cdiv(N, 8), 256, (size_t)nr * K * sizeof(float), st>>>(in + (size_t)r0 * ldin, ldin, W, b, out + (size_t)r0 * ldo, ldo, nr, N, K,
-                                                                    silu_in, in_mod, act);
-    DVD_LAUNCH_CHECK("k_gemv");
-  }
-  return 0;
+  GemvProb pr{{in, in}, {W, W}, {b, b}, {out, out}};
+  return gemv_launch(pr, 1, ldin, ldo, rows, N, K, silu_in, in_mod, act, st);
+}
+// two independent layers of the same shape in one launch: out0 = act(W0 in0 + b0), out1 = act(W1 in1 + b1)
+int gemv_pair(const float* in0, const float* in1, int ldin, const float* W0, const float* W1, const float* b0, const float* b1, float* out0,
+              float* out1, int ldo, int rows, int N, int K, int act, cudaStream_t st) {
+  DVD_REQUIRE(in0 && in1 && W0 && W1 && out0 && out1 && N > 0 && K > 0 && K % 4 == 0 && K <= 1536, "gemv_pair: bad args (K=%d)", K);
+  DVD_REQUIRE(((reinterpret_cast<uintptr_t>(W0) | reinterpret_cast<uintptr_t>(W1)) & 15) == 0, "gemv_pair: W must be 16-byte aligned");
+  GemvProb pr{{in0, in1}, {W0, W1}, {b0, b1}, {out0, out1}};
+  return gemv_launch(pr, 2, ldin, ldo, rows, N, K, 0, 0, act, st);
 }
 
 __global__ void k_timestep_embedding(const float* __restrict__ t, float* __restrict__ out, int rows) {

@@ -46,6 +46,8 @@ int softmax_rows(float* S, long long rows, int n, cudaStream_t st);
 // f = SiLU if silu_in; input index taken modulo in_mod (t.repeat(1,4), CM:331) if in_mod > 0.
 int gemv(const float* in, int ldin, const float* W, const float* b, float* out, int ldo, int rows, int N, int K,
          int silu_in, int in_mod, int act, cudaStream_t st);
+int gemv_pair(const float* in0, const float* in1, int ldin, const float* W0, const float* W1, const float* b0, const float* b1, float* out0,
+              float* out1, int ldo, int rows, int N, int K, int act, cudaStream_t st);
 
 // sinusoidal timestep embedding (CM:111-134): out[r, 0:128]=cos, [128:256]=sin
 int timestep_embedding(const float* t, float* out, int rows, cudaStream_t st);
