@@ -1,5 +1,2 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python bench.py --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])"
+DVD_GEMM_V1=1 timeout 300 python tools/gemm_trace.py > gpurun_out/r28_gemm_trace.txt 2>&1
