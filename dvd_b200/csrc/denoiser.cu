@@ -22,59 +22,100 @@ struct Workspace {
   // per step
   float *a_r, *xe, *r, *qn, *q, *kv_r, *xo, *xs, *hmod, *qkv, *h1, *X, *pe, *hd, *qkv_d, *att_d, *f1, *f2, *S;
   float *flow[2], *xbuf[2], *pred;
+  float* final_flow;                       // [docs * n_hyp, 2, 64, 64]: last pred_xstart of every hypothesis (input of the mean)
   // bf16 operand staging (DVD_PREC_BF16)
   __nv_bfloat16 *a_stat16, *ctx16[3], *a_r16, *r16, *qn16, *xo16, *hmod16, *h116, *hd16, *att_d16, *f116, *f216;
   __nv_bfloat16 *q16, *kv_static16[3], *kv_r16, *qkv16, *qkv_d16;       // attention operands (Q, K row-major)
   __nv_bfloat16 *vt_static16[3], *vt_r16, *vt_qkv16, *vt_d16;            // V^T [sample, C_v, 1024] written by the GEMM epilogues
   size_t s_floats;
+  size_t step_off;                         // offset of the per-step region
   size_t total_bytes;
 };
 
 constexpr size_t kSChunkSamples = 8;      // (sample, 6 heads) pairs per fp32 attention chunk
 
-static Workspace carve(void* base, int docs, int n_hyp, int precision) {
-  Workspace w{};
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return base ? (char*)base + o : (char*)nullptr; };
-  auto F = [&](size_t n) { return (float*)take(n * 4); };
-  auto H = [&](size_t n) { return (__nv_bfloat16*)take(n * 2); };
-  const size_t N = (size_t)docs * n_hyp, M = N * 1024, Md = (size_t)docs * 1024;
-  const bool tc = precision == DVD_PREC_BF16;
-  w.y4 = F((size_t)docs * 512 * 512 * 4);
-  w.pyrP = F((size_t)docs * 512 * 512 * 64);
-  w.pyrQ = F((size_t)docs * 512 * 512 * 64);
-  w.feat = F((size_t)docs * 4096 * 256);
-  w.a_stat = F(Md * 1536);
-  for (int i = 0; i < 3; ++i) w.ctx[i] = F(Md * 384);
-  for (int i = 0; i < 3; ++i) w.kv_static[i] = F(Md * 768);
-  w.a_r = F(M * 1032);
-  w.xe = F(M * 384); w.r = F(M * 384); w.qn = F(M * 384); w.q = F(M * 384);
-  w.kv_r = F(M * 768);
-  w.xo = F(4 * M * 384); w.xs = F(4 * M * 384); w.hmod = F(4 * M * 384);
-  w.qkv = F(4 * M * 1152);
-  w.h1 = F(4 * M * 1536);
-  w.X = F(M * 1536);
-  w.pe = F(N * 1536 * (1 + 32 + 4));      // mean | 32 partials | hs1 hs ws1 ws
-  w.hd = F(M * 1536); w.qkv_d = F(M * 4608); w.att_d = F(M * 1536);
-  w.f1 = F(M * 2048); w.f2 = F(M * 2048);
+struct Carver {
+  char* base; size_t off;
+  char* take(size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return base ? base + o : nullptr; }
+  float* F(size_t n) { return (float*)take(n * 4); }
+  __nv_bfloat16* H(size_t n) { return (__nv_bfloat16*)take(n * 2); }
+};
+
+// per-document buffers (written by static_forward, read by every step of every hypothesis) + the gathered final flows
+static void carve_static(Carver& k, Workspace& w, int docs, int n_hyp, bool tc) {
+  const size_t Md = (size_t)docs * 1024;
+  w.y4 = k.F((size_t)docs * 512 * 512 * 4);
+  w.pyrP = k.F((size_t)docs * 512 * 512 * 64);
+  w.pyrQ = k.F((size_t)docs * 512 * 512 * 64);
+  w.feat = k.F((size_t)docs * 4096 * 256);
+  w.a_stat = k.F(Md * 1536);
+  for (int i = 0; i < 3; ++i) w.ctx[i] = k.F(Md * 384);
+  for (int i = 0; i < 3; ++i) w.kv_static[i] = k.F(Md * 768);
+  w.final_flow = k.F((size_t)docs * n_hyp * 8192);
+  if (tc) {
+    w.a_stat16 = k.H(Md * 1536);
+    for (int i = 0; i < 3; ++i) w.ctx16[i] = k.H(Md * 384);
+    for (int i = 0; i < 3; ++i) w.kv_static16[i] = k.H(Md * 768);
+    for (int i = 0; i < 3; ++i) w.vt_static16[i] = k.H(Md * 384);
+  }
+}
+
+// per-step buffers of a group of docs * n_hyp samples
+static void carve_step(Carver& k, Workspace& w, int docs, int n_hyp, bool tc) {
+  const size_t N = (size_t)docs * n_hyp, M = N * 1024;
+  w.a_r = k.F(M * 1032);
+  w.xe = k.F(M * 384); w.r = k.F(M * 384); w.qn = k.F(M * 384); w.q = k.F(M * 384);
+  w.kv_r = k.F(M * 768);
+  w.xo = k.F(4 * M * 384); w.xs = k.F(4 * M * 384); w.hmod = k.F(4 * M * 384);
+  w.qkv = k.F(4 * M * 1152);
+  w.h1 = k.F(4 * M * 1536);
+  w.X = k.F(M * 1536);
+  w.pe = k.F(N * 1536 * (1 + 32 + 4));      // mean | 32 partials | hs1 hs ws1 ws
+  w.hd = k.F(M * 1536); w.qkv_d = k.F(M * 4608); w.att_d = k.F(M * 1536);
+  w.f1 = k.F(M * 2048); w.f2 = k.F(M * 2048);
   size_t chunk = N < kSChunkSamples ? N : kSChunkSamples;
   w.s_floats = tc ? 0 : (size_t)4 * chunk * kHeads * 1024 * 1024;        // up to 4 streams x chunk samples
-  w.S = F(w.s_floats);
-  for (int i = 0; i < 2; ++i) { w.flow[i] = F(N * 8192); w.xbuf[i] = F(N * 8192); }
-  w.pred = F(N * 8192);
+  w.S = k.F(w.s_floats);
+  for (int i = 0; i < 2; ++i) { w.flow[i] = k.F(N * 8192); w.xbuf[i] = k.F(N * 8192); }
+  w.pred = k.F(N * 8192);
   if (tc) {
-    w.a_stat16 = H(Md * 1536);
-    for (int i = 0; i < 3; ++i) w.ctx16[i] = H(Md * 384);
-    w.a_r16 = H(M * 1032);
-    w.r16 = H(M * 384); w.qn16 = H(M * 384); w.xo16 = H(4 * M * 384); w.hmod16 = H(4 * M * 384);
-    w.h116 = H(4 * M * 1536); w.hd16 = H(M * 1536); w.att_d16 = H(M * 1536); w.f116 = H(M * 2048); w.f216 = H(M * 2048);
-    w.q16 = H(M * 384); w.kv_r16 = H(M * 768); w.qkv16 = H(4 * M * 1152); w.qkv_d16 = H(M * 4608);
-    for (int i = 0; i < 3; ++i) w.kv_static16[i] = H(Md * 768);
-    for (int i = 0; i < 3; ++i) w.vt_static16[i] = H(Md * 384);
-    w.vt_r16 = H(M * 384); w.vt_qkv16 = H(4 * M * 384); w.vt_d16 = H(M * 1536);
+    w.a_r16 = k.H(M * 1032);
+    w.r16 = k.H(M * 384); w.qn16 = k.H(M * 384); w.xo16 = k.H(4 * M * 384); w.hmod16 = k.H(4 * M * 384);
+    w.h116 = k.H(4 * M * 1536); w.hd16 = k.H(M * 1536); w.att_d16 = k.H(M * 1536); w.f116 = k.H(M * 2048); w.f216 = k.H(M * 2048);
+    w.q16 = k.H(M * 384); w.kv_r16 = k.H(M * 768); w.qkv16 = k.H(4 * M * 1152); w.qkv_d16 = k.H(M * 4608);
+    w.vt_r16 = k.H(M * 384); w.vt_qkv16 = k.H(4 * M * 384); w.vt_d16 = k.H(M * 1536);
   }
-  w.total_bytes = off;
+}
+
+// One document with >= 2 hypotheses may be sampled as two concurrent groups (dvd_sample): their per-step buffers are carved one after
+// the other in the same region, which must therefore be large enough for either layout.
+static bool can_split(int docs, int n_hyp) { return docs == 1 && n_hyp >= 2; }
+
+static Workspace carve(void* base, int docs, int n_hyp, int precision) {
+  Workspace w{};
+  const bool tc = precision == DVD_PREC_BF16;
+  Carver k{(char*)base, 0};
+  carve_static(k, w, docs, n_hyp, tc);
+  w.step_off = k.off;
+  carve_step(k, w, docs, n_hyp, tc);
+  w.total_bytes = k.off;
+  if (can_split(docs, n_hyp)) {
+    Carver k2{nullptr, w.step_off};
+    Workspace t{};
+    carve_step(k2, t, 1, n_hyp / 2, tc);
+    carve_step(k2, t, 1, n_hyp - n_hyp / 2, tc);
+    if (k2.off > w.total_bytes) w.total_bytes = k2.off;
+  }
   return w;
+}
+
+// per-step buffers of one hypothesis group, carved at `off` (updated) of the same workspace; static buffers shared with `master`
+static Workspace carve_group(const Workspace& master, void* base, size_t& off, int n_hyp_g, bool tc) {
+  Workspace g = master;
+  Carver k{(char*)base, off};
+  carve_step(k, g, 1, n_hyp_g, tc);
+  off = k.off;
+  return g;
 }
 
 // ------------------------------------------------------------------------------------------ fp32 attention (GEMM + softmax + GEMM)
@@ -460,6 +501,43 @@ extern "C" int dvd_hyp_mean_clamp(const float* pred_x0, float* out, int docs, in
   return hyp_mean_clamp(pred_x0, out, docs, n_hyp, (cudaStream_t)stream);
 }
 
+// The S-step DDIM loop of one group of hypotheses (GD:574-633); leaves the last pred_xstart of the group in `final_flow`.
+static int sample_group(const Ctx& c, const float* x_T, const float* init_flow0, const float* tables, const float* t_scaled_host,
+                        const float* ddim_a_host, const float* ddim_b_host, int S, const float* init_feat0, float* final_flow, int it_begin,
+                        int it_end, const float*& x, int& cur) {
+  const Workspace& s = c.ws; cudaStream_t st = c.st;
+  const int n_hyp = c.n_hyp;
+  if (it_begin == 0) {
+    // GD:574: every kwarg (incl. init_flow) is repeated n_hyp times
+    for (int d = 0; d < c.docs; ++d)
+      for (int h = 0; h < n_hyp; ++h)
+        DVD_CUDA(cudaMemcpyAsync(s.flow[0] + ((size_t)d * n_hyp + h) * 8192, init_flow0 + (size_t)d * 8192, 8192 * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+    x = x_T; cur = 0;
+  }
+  for (int it = it_begin; it < it_end; ++it) {
+    // CM:597-598: while the rescaled t > 600 the model overrides init_feat with the un-warped feature.
+    // GD:618-624: from the second iteration on, init_flow = previous pred_xstart and init_feat = warp(feat).
+    // First iteration with t <= 600 (only possible for S < 3): the caller's init_feat (zeros at EV:167) is used.
+    int feat_mode = t_scaled_host[it] > 600.0f ? FEAT_ASIS : (it == 0 ? FEAT_EXPLICIT_OR_ZERO : FEAT_WARP);
+    float* xn = s.xbuf[it & 1];
+    float* pred = (it + 1 == S) ? final_flow : s.flow[cur ^ 1];      // pred of this step is init_flow of the next one
+    DVD_TRY(denoise_step(c, x, s.flow[cur], feat_mode == FEAT_EXPLICIT_OR_ZERO ? init_feat0 : nullptr, n_hyp, feat_mode,
+                         tables + (size_t)it * DVD_TABLE_ROW, ddim_a_host[it], ddim_b_host[it], pred, it + 1 < S ? xn : nullptr));
+    x = xn; cur ^= 1;
+  }
+  return 0;
+}
+
+// second stream + fork / join events of the two-group mode (created on first use, i.e. in the caller's eager warm-up call)
+struct SplitStreams { cudaStream_t aux = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static thread_local SplitStreams g_split;
+static int split_mode() {       // DVD_HYP_SPLIT=1 samples the hypotheses of a single document as two concurrent chains (off by default)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DVD_HYP_SPLIT"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 extern "C" int dvd_sample(const dvd_weights_t* w, void* workspace, size_t workspace_bytes, int docs, int n_hyp, int precision,
                           const float* x_T, const float* init_flow0, const float* tables, const float* t_scaled_host,
                           const float* ddim_a_host, const float* ddim_b_host, int S, const float* init_feat0, float* map_out,
@@ -467,25 +545,38 @@ extern "C" int dvd_sample(const dvd_weights_t* w, void* workspace, size_t worksp
   Ctx c;
   DVD_TRY(make_ctx(c, w, workspace, workspace_bytes, docs, n_hyp, precision, stream));
   DVD_REQUIRE(x_T && init_flow0 && tables && t_scaled_host && ddim_a_host && ddim_b_host && map_out && S > 0, "sample: bad args");
-  const Workspace& s = c.ws; cudaStream_t st = c.st;
-  // GD:574: every kwarg (incl. init_flow) is repeated n_hyp times
-  for (int d = 0; d < docs; ++d)
-    for (int h = 0; h < n_hyp; ++h)
-      DVD_CUDA(cudaMemcpyAsync(s.flow[0] + ((size_t)d * n_hyp + h) * 8192, init_flow0 + (size_t)d * 8192, 8192 * sizeof(float),
-                               cudaMemcpyDeviceToDevice, st));
-  const float* x = x_T;
-  int cur = 0;
-  for (int it = 0; it < S; ++it) {
-    // CM:597-598: while the rescaled t > 600 the model overrides init_feat with the un-warped feature.
-    // GD:618-624: from the second iteration on, init_flow = previous pred_xstart and init_feat = warp(feat).
-    // First iteration with t <= 600 (only possible for S < 3): the caller's init_feat (zeros at EV:167) is used.
-    int feat_mode = t_scaled_host[it] > 600.0f ? FEAT_ASIS : (it == 0 ? FEAT_EXPLICIT_OR_ZERO : FEAT_WARP);
-    float* xn = s.xbuf[it & 1];
-    float* pred = s.flow[cur ^ 1];               // pred of this step is init_flow of the next one
-    DVD_TRY(denoise_step(c, x, s.flow[cur], feat_mode == FEAT_EXPLICIT_OR_ZERO ? init_feat0 : nullptr, n_hyp, feat_mode,
-                         tables + (size_t)it * DVD_TABLE_ROW, ddim_a_host[it], ddim_b_host[it], pred, it + 1 < S ? xn : nullptr));
-    x = xn; cur ^= 1;
+  cudaStream_t st = c.st;
+  // Experiment (DVD_HYP_SPLIT=1, off by default): the hypotheses of a document are independent until the final mean (GD:574), so they can be
+  // sampled as TWO concurrent chains on two streams (fork / join with events, capturable into one CUDA graph) in the hope that one
+  // chain's prologues, epilogues and launch gaps overlap the other's main loops.  Results are identical (every kernel is per-sample),
+  // but measured SLOWER on B200 (3.94 vs 3.70 ms per document): the half-size kernels are latency bound and take almost as long as the
+  // full-size ones.  Not used while the kernel-class profiler is on.
+  if (can_split(docs, n_hyp) && split_mode() && !g_prof.on && !init_feat0) {
+    if (!g_split.aux) {
+      DVD_CUDA(cudaStreamCreateWithFlags(&g_split.aux, cudaStreamNonBlocking));
+      DVD_CUDA(cudaEventCreateWithFlags(&g_split.fork, cudaEventDisableTiming));
+      DVD_CUDA(cudaEventCreateWithFlags(&g_split.join, cudaEventDisableTiming));
+    }
+    const int h0 = n_hyp / 2;
+    size_t off = c.ws.step_off;
+    Ctx g[2] = {c, c};
+    g[0].n_hyp = h0; g[0].ws = carve_group(c.ws, workspace, off, h0, c.tc());
+    g[1].n_hyp = n_hyp - h0; g[1].ws = carve_group(c.ws, workspace, off, n_hyp - h0, c.tc());
+    g[1].st = g_split.aux;
+    DVD_CUDA(cudaEventRecord(g_split.fork, st));
+    DVD_CUDA(cudaStreamWaitEvent(g_split.aux, g_split.fork, 0));
+    const float* x[2] = {nullptr, nullptr}; int cur[2] = {0, 0};
+    for (int it = 0; it < S; ++it)                       // enqueue the two chains step by step so that both streams stay fed in eager mode
+      for (int k = 0; k < 2; ++k) {
+        const int hb = k ? h0 : 0;
+        DVD_TRY(sample_group(g[k], x_T + (size_t)hb * 8192, init_flow0, tables, t_scaled_host, ddim_a_host, ddim_b_host, S, nullptr,
+                             c.ws.final_flow + (size_t)hb * 8192, it, it + 1, x[k], cur[k]));
+      }
+    DVD_CUDA(cudaEventRecord(g_split.join, g_split.aux));
+    DVD_CUDA(cudaStreamWaitEvent(st, g_split.join, 0));
+    return hyp_mean_clamp(c.ws.final_flow, map_out, docs, n_hyp, st);
   }
-  const float* flow = s.flow[cur];
-  return hyp_mean_clamp(flow, map_out, docs, n_hyp, st);
+  const float* x = nullptr; int cur = 0;
+  DVD_TRY(sample_group(c, x_T, init_flow0, tables, t_scaled_host, ddim_a_host, ddim_b_host, S, init_feat0, c.ws.final_flow, 0, S, x, cur));
+  return hyp_mean_clamp(c.ws.final_flow, map_out, docs, n_hyp, st);
 }

@@ -334,6 +334,30 @@ def test_document_batch_equals_single_documents(dev, models, prec):
         assert float((both[j:j + 1] - one).abs().max()) < (1e-5 if prec == "fp32" else 1e-3)
 
 
+def test_two_chain_hypothesis_split_is_identical(dev, models, golden_dir):
+    """DVD_HYP_SPLIT=1 (the two hypotheses of a document sampled as two concurrent chains on two streams) gives the same map as
+    the batched default: compared through the reference's golden sample (the env is read once per process, hence the subprocess)."""
+    import subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, torch, numpy as np; sys.path.insert(0, %r)\n"
+            "from oracle import synth; from dvd_b200.model import DiT; from dvd_b200.sampler import create_gaussian_diffusion\n"
+            "m = DiT(precision='fp32'); m.load_state_dict(synth.make_state_dict(1234, live_only=True), strict=False); m = m.cuda().eval()\n"
+            "inp = {k: v.cuda() for k, v in synth.make_doc_inputs(0, H=96, W=128).items() if k != 'photo'}\n"
+            "kw = {'init_flow': inp['init_flow'], 'src_feat': None, 'src_64': None, 'y512': inp['y512'], 'tmode': 'stage_1_dit_cross',\n"
+            "      'mask_cat': inp['mask_cat'], 'init_feat': inp['init_feat'], 'iter': True, 'mask_y512': inp['mask_y512'], 'line_msk': inp['line_msk']}\n"
+            "d = create_gaussian_diffusion(steps=3, noise_schedule='cosine', predict_xstart=True, rescale_timesteps=True,\n"
+            "                              rescale_learned_sigmas=True, timestep_respacing='')\n"
+            "out, _ = d.ddim_sample_loop(m, (1, 2, 64, 64), clip_denoised=False, model_kwargs=kw, eta=0.0, n_batch=2, time_variant=True, x_T=inp['x_T'])\n"
+            "torch.cuda.synchronize(); np.save(sys.argv[1], out.cpu().numpy())\n" % root)
+    with tempfile.TemporaryDirectory() as td:
+        f = os.path.join(td, "split.npy")
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, DVD_HYP_SPLIT="1"), timeout=600)
+        split = np.load(f)
+    g = np.load(os.path.join(golden_dir, "sample_S3_doc0.npz"))
+    d = np.abs(split - g["sample"])
+    assert float(d.mean()) < FP32_MEAN and float(d.max()) < FP32_MAX, (float(d.mean()), float(d.max()))
+
+
 def test_seeded_noise_consumption_matches_reference_order(dev, models):
     """Without x_T the sampler draws randn(shape) then randn(n_batch, ...) like gaussian_diffusion.py:559-569."""
     inp = synth.make_doc_inputs(0, with_photo=False)
