@@ -148,6 +148,27 @@ def test_unwarp_staged_and_gather_tiles_agree_with_oracle(dev, deg, zoom):
     assert int((u8[0].int() - ref[0].permute(1, 2, 0).clamp(0, 255).int()).abs().max()) <= 1
 
 
+def test_unwarp_tma_batched_and_single_channel(dev):
+    """The persistent TMA-staged kernel walks tiles of several photos (tile -> image decode, per-image maps, plane index of the
+    tensor maps) and handles C = 1: a batch equals the single calls bit for bit and matches the oracle."""
+    from dvd_b200 import dewarp_fullres
+    H, W = 600, 800
+    maps = torch.cat([_rotation_map(4.0) + 0.3 * synth.make_map64(11, "smooth"), 0.5 * synth.make_map64(12, "smooth"),
+                      _rotation_map(-8.0, 1.1)])
+    photos = torch.cat([synth.make_photo(H, W, 40 + i, "noise" if i % 2 else "page") for i in range(3)])
+    both = dewarp_fullres(maps.to(dev), photos.to(dev))
+    for i in range(3):
+        one = dewarp_fullres(maps[i:i + 1].to(dev), photos[i:i + 1].to(dev))
+        assert torch.equal(both[i:i + 1], one)
+        ref = O.unwarp(maps[i:i + 1], photos[i:i + 1])
+        assert psnr(one.cpu(), ref) >= 60.0 and float((one.cpu() - ref).abs().max()) < 0.5
+    gray = photos[:, :1].contiguous()
+    g = dewarp_fullres(maps.to(dev), gray.to(dev)).cpu()
+    assert psnr(g, O.unwarp(maps, gray)) >= 60.0
+    g8 = dewarp_fullres(maps.to(dev), gray.to(dev), out_uint8=True).cpu()             # fp32 in, uint8 HWC out through the TMA store
+    assert int((g8.int() - O.unwarp(maps, gray).permute(0, 2, 3, 1).clamp(0, 255).int()).abs().max()) <= 1
+
+
 def test_unwarp_tma_and_gather_kernels_agree(dev):
     """The TMA-staged kernel (default for fp32 photos, DVD_UNWARP_TMA_U8=1 for uint8 photos) and the global-gather kernel
     (DVD_UNWARP_NO_TMA=1) give the same image up to ulp-level coordinate differences."""
