@@ -10,10 +10,13 @@
 // 6 B/px (uint8 HWC).  The reference moves ~88 B/px (two materialised fields, five elementwise
 // passes, grid read, gather, store).
 //
-// Mapping: one thread = 4 consecutive output pixels of one row -> 128-bit coalesced stores per
-// channel plane; a CTA covers a 128 x 8 pixel tile so that the gathered source footprint (the map
-// is a smooth near-identity field) stays inside a few KB of L1.  The 64x64 coarse map (32 KB) is
-// read through the read-only path and stays L1/L2 resident.
+// Three kernels, one arithmetic:
+//   k_unwarp_tma   fp32 photos (the roofline kernel): persistent CTAs, source windows staged in shared memory by TMA, output tiles
+//                  leaving through TMA stores (see the comment above the kernel);
+//   k_unwarp_fast  uint8 photos and shapes the TMA path does not take: a CTA covers a 128 x 8 pixel tile, per-tile coefficient tables
+//                  and the vertically pre-blended coarse-map window in shared memory, gathers through L1;
+//   k_unwarp       fully general fallback (tiny photos / huge maps).
+// The 64x64 coarse map (32 KB) is read through the read-only path and stays L1/L2 resident.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>

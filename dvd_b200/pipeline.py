@@ -88,7 +88,7 @@ class DewarpPipeline:
     SAMPLING_KEYS = ("y512", "mask_cat", "mask_y512", "line_msk", "x_T")
 
     def run_device(self, d: dict) -> torch.Tensor:
-        """The ~245 kernel launches of one batch are captured once per set of input buffers into two CUDA graphs (sampling,
+        """The ~230 kernel launches of one batch are captured once per set of input buffers into two CUDA graphs (sampling,
         unwarp) and replayed (the library never allocates or synchronises, so every entry point is capturable)."""
         with torch.cuda.device(self.dev):
             self._run("sampling", d, self.SAMPLING_KEYS, self._enqueue_sampling)
