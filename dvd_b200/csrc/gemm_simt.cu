@@ -174,6 +174,7 @@ int gemm_f32(const GemmParams& p, int amode, int bmode, int batch, cudaStream_t 
   else DVD_REQUIRE(p.convC % 4 == 0 && p.K == 9 * p.convC, "gemm_f32: conv needs C %% 4 == 0 and K == 9C");
   DVD_REQUIRE(p.ldb % 4 == 0, "gemm_f32: ldb %% 4");
   const bool narrow = (p.N <= 64);
+  DVD_REQUIRE(cdiv(p.M, BM) <= 65535, "gemm_f32: M = %d needs more than 65535 row tiles (the fp32 parity mode handles up to 31 documents per call)", p.M);
   dim3 grid(cdiv(p.N, narrow ? 64 : 128), cdiv(p.M, BM), batch);
   DVD_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_f32: grid too large");
 #define DVD_GEMM_CASE(AM, BMd)                                                         \

@@ -110,7 +110,7 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
 #ifdef DVD_GEMM_TRACE
 __device__ unsigned long long g_gemm_trace[2048][8];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define DVD_TRACE(slot) do { g_gemm_trace[(blockIdx.y * gridDim.x + blockIdx.x) & 2047][slot] = gtime(); } while (0)
+#define DVD_TRACE(slot) do { g_gemm_trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) & 2047][slot] = gtime(); } while (0)
 #else
 #define DVD_TRACE(slot) do { } while (0)
 #endif
@@ -155,7 +155,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
+  // M tiles beyond the 65535 limit of gridDim.y (the 512x512 pyramid levels of >= 32 documents) are folded into gridDim.z
+  const int m0 = (blockIdx.z * gridDim.y + blockIdx.y) * TBM, n0 = blockIdx.x * BN;
+  if (m0 >= M) return;                                  // whole CTA (ragged last z-slice)
   const int nkb = (K + TBK - 1) / TBK;
 
   pdl_trigger();                                        // the next kernel of the stream may start its own prologue
@@ -367,7 +369,8 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
     DVD_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
     attr_set = true;
   }
-  dim3 grid(cdiv(N, BN), cdiv(M, TBM));
+  const int my = cdiv(M, TBM), gy = my > 32768 ? 32768 : my;
+  dim3 grid(cdiv(N, BN), gy, cdiv(my, gy));
   DVD_CUDA(launch_pdl(1, k_gemm_tc<BN, CONV>, grid, dim3(TC_THREADS), (size_t)TcCfg<BN>::SMEM, st, tmA, tmB, M, N, K, e, cg));
   DVD_LAUNCH_CHECK("k_gemm_tc");
   return 0;
@@ -435,7 +438,7 @@ int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ld
     const int bn = wide ? 256 : 128;
     const int gx = N / bn, gy = M / 128;
     int cl = 0;
-    if (N % bn == 0 && cl_env != 0) {
+    if (N % bn == 0 && cl_env != 0 && gy <= 32768) {
       if (gx % 2 == 0 && gy % 2 == 0) cl = 22; else if (gy % 2 == 0) cl = 12; else if (gx % 2 == 0) cl = 21;
       if (cl_env == 12 && gy % 2 == 0) cl = 12;
       if (cl_env == 21 && gx % 2 == 0) cl = 21;

@@ -253,6 +253,23 @@ def test_gemm_bf16_tcgen05(dev, M, N, K):
     assert float((Cg - ref).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max()))
 
 
+def test_gemm_bf16_more_row_tiles_than_grid_y(dev):
+    """M / 128 > 65535 row tiles (the 512x512 pyramid levels of >= 32 documents in flight): the tile index is folded into
+    gridDim.z, with a ragged last z-slice."""
+    from dvd_b200 import _lib
+    M, N, K = (65536 + 3) * 128, 64, 64
+    g = torch.Generator(device=dev).manual_seed(5)
+    A = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device=dev, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device=dev, generator=g)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().dvd_gemm_bf16(_lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(b), _lib.ptr(out), None, M, N, K, _lib.stream_ptr()), "gemm")
+    torch.cuda.synchronize()
+    for r0 in (0, 32768 * 128 - 64, 65535 * 128 - 64, 65536 * 128 - 64, M - 256):      # start, z-slice boundaries, ragged tail
+        ref = A[r0:r0 + 256].float() @ W.float().t() + b
+        assert float((out[r0:r0 + 256].float() - ref).abs().max()) < 3e-2 * max(1.0, float(ref.abs().max())), r0
+
+
 def _run_attn(dev, B, H, T, d, prec):
     from dvd_b200 import _lib
     g = torch.Generator().manual_seed(B + H + d)
