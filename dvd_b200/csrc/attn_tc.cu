@@ -1,6 +1,6 @@
 // Fused attention on tcgen05: O = softmax(scale * Q K^T) V for one (sample, head, 128-query tile) per CTA.
 //
-//   S = Q K^T  : UMMA M=128 (queries) x N=64 (keys) x K=d, accumulator in TMEM (two S buffers)
+//   S = Q K^T  : UMMA M=128 (queries) x N=64 (keys) x K=d, accumulator in TMEM (two S buffers for d = 256, one for d = 64)
 //   softmax    : 8 warps; TMEM lane == query row, and each row is shared by TWO threads (one per 32-key half, the two warps that
 //                may access the same TMEM lane quarter): tcgen05.ld S, row max exchanged through smem + a 64-thread named barrier,
 //                exp2 / partial sums in fp32, P (bf16) written to shared memory in the 128-byte-swizzled K-major layout
@@ -25,15 +25,19 @@ constexpr int ATHREADS = 320;
 
 template <int D>
 struct AttnCfg {
-  static constexpr int STAGES = (D == 64) ? 4 : 2;
+  // d = 64 (DiT block): ONE S buffer, 128 TMEM columns and a 2-stage ring, so that three CTAs share an SM and the 384-CTA launches of
+  // the DiT block fit one wave (444 slots) instead of 1.3 waves of two CTAs per SM; the co-resident CTAs overlap each other's softmax.
+  // d = 256 (decoder): O alone needs 256 columns -> one CTA per SM, two S buffers so that QK^T(t+1) overlaps softmax(t).
+  static constexpr int NSB = (D == 64) ? 1 : 2;
+  static constexpr int STAGES = 2;
   static constexpr int Q_BYTES = AQ * D * 2;
   static constexpr int K_BYTES = AKV * D * 2, V_BYTES = D * AKV * 2;
   static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
   static constexpr int P_BYTES = AQ * AKV * 2;
   static constexpr int X_BYTES = 2 * 2 * AQ * 4;                // row-max / row-sum exchange: [parity][half][row]
   static constexpr int SMEM = Q_BYTES + STAGES * STAGE_BYTES + P_BYTES + X_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;      // 2 x 64 (S) + D (O), rounded to a power of two
-  static constexpr int O_COL = 2 * AKV;
+  static constexpr int TMEM_COLS = (D == 64) ? 128 : 512;      // NSB x 64 (S) + D (O), rounded to a power of two
+  static constexpr int O_COL = NSB * AKV;
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -56,7 +60,7 @@ struct AttnCtx {
 };
 
 template <int D>
-__global__ void __launch_bounds__(ATHREADS) k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ AttnCtx cx, int nsamp,
+__global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ AttnCtx cx, int nsamp,
                                                       int ldo, int T, int heads, float scale_log2) {
   using Cfg = AttnCfg<D>;
   constexpr int ST = Cfg::STAGES;
@@ -130,9 +134,9 @@ __global__ void __launch_bounds__(ATHREADS) k_attn_tc(const __grid_constant__ CU
       constexpr uint32_t idesc_pv = make_idesc_bf16(AQ, D);       // 128 x D
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       auto issue_qk = [&](int t) {
-        const int s = t % ST, b = t & 1;
+        const int s = t % ST, b = t % Cfg::NSB;
         mbar_wait(&k_full[s], (t / ST) & 1);
-        mbar_wait(&s_empty[b], ((t >> 1) & 1) ^ 1);
+        mbar_wait(&s_empty[b], ((t / Cfg::NSB) & 1) ^ 1);
         fence_after_sync();
         const uint32_t k_addr = smem_u32(sKV + s * Cfg::STAGE_BYTES);
 #pragma unroll
@@ -167,8 +171,8 @@ __global__ void __launch_bounds__(ATHREADS) k_attn_tc(const __grid_constant__ CU
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     float m = -INFINITY, l = 0.f;                                 // m is identical in both halves; l is this half's partial sum
     for (int t = 0; t < nt; ++t) {
-      const int b = t & 1;
-      mbar_wait(&s_full[b], (t >> 1) & 1);
+      const int b = t % Cfg::NSB;
+      mbar_wait(&s_full[b], (t / Cfg::NSB) & 1);
       fence_after_sync();
       uint32_t s0[32];
       tmem_ld_32x32(lane_base + b * AKV + half * 32, s0);
