@@ -46,8 +46,7 @@ class DewarpPipeline:
         self.use_graph = os.environ.get("DVD_NO_GRAPH", "0") != "1"
         self._graphs = {}                  # input-pointer tuple -> (CUDAGraph, kernels per replay, keep-alive dict)
         self.kernel_launches = 0           # kernels of libdvd_b200 launched (or replayed) through this pipeline
-        self._copy_stream = None
-        self._photo_ready = None
+        self._slots = None                 # double-buffered host I/O state (submit_host / wait)
 
     # ---- device-resident inputs: dict with y512, mask_cat, mask_y512, line_msk, x_T, photo_u8 (all on self.dev)
     def _enqueue_sampling(self, d: dict):
@@ -57,7 +56,8 @@ class DewarpPipeline:
 
     def _enqueue_unwarp(self, d: dict):
         """fused upsample + affine + bilinear unwarp of the full-resolution photo, on the current stream."""
-        _lib.check(self.lib.dvd_unwarp_u8(_lib.ptr(d["photo_u8"]), _lib.ptr(self.map64), _lib.ptr(self.out_u8), self.docs, 3,
+        out = d.get("out_u8", self.out_u8)
+        _lib.check(self.lib.dvd_unwarp_u8(_lib.ptr(d["photo_u8"]), _lib.ptr(self.map64), _lib.ptr(out), self.docs, 3,
                                           self.H, self.W, 64, 64, AFFINE, _lib.stream_ptr()), "dvd_unwarp_u8")
 
     def _graph(self, which: str, d: dict, keys, fn):
@@ -96,25 +96,62 @@ class DewarpPipeline:
         return self.out_u8
 
     # ---- pinned-host inputs -> host uint8 image (H2D and D2H inside the call)
-    def run_host(self, h: dict) -> torch.Tensor:
-        """The photo is only needed by the last kernel, so its upload runs on a second stream underneath the sampling graph."""
+    def _make_slots(self):
+        """Two sets of device input / output buffers + copy streams: the uploads of batch i+1 and the download of batch i run
+        underneath the kernels of the batch in between (the kernels themselves stay on the caller's stream, one batch at a time)."""
+        self._h2d = torch.cuda.Stream(device=self.dev)
+        self._d2h = torch.cuda.Stream(device=self.dev)
+        self._slots = []
+        for _ in range(2):
+            buf = {k: torch.empty_like(v) for k, v in self.buf.items()}
+            buf["out_u8"] = torch.empty_like(self.out_u8)
+            self._slots.append({"buf": buf, "out_host": torch.empty_like(self.out_host).pin_memory(), "used": False,
+                                "ev_in": torch.cuda.Event(), "ev_photo": torch.cuda.Event(), "ev_done": torch.cuda.Event(),
+                                "ev_out": torch.cuda.Event()})
+        self._submitted = 0
+
+    def submit_host(self, h: dict) -> int:
+        """Enqueue one batch (pinned host inputs) without waiting for it; returns a ticket for `wait`.  At most two batches may be
+        outstanding (a ticket must be waited for before the second-next submit).  The photo is only needed by the last kernel, so
+        its upload also runs underneath this batch's own sampling."""
         with torch.cuda.device(self.dev):
+            if self._slots is None:
+                self._make_slots()
             main = torch.cuda.current_stream()
-            if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream(device=self.dev)
-                self._photo_ready = torch.cuda.Event()
-            for k in self.SAMPLING_KEYS:
-                self.buf[k].copy_(h[k], non_blocking=True)
-            self._copy_stream.wait_stream(main)                    # the previous call's unwarp has finished reading photo_u8
-            with torch.cuda.stream(self._copy_stream):
-                self.buf["photo_u8"].copy_(h["photo_u8"], non_blocking=True)
-                self._photo_ready.record()
-            self._run("sampling", self.buf, self.SAMPLING_KEYS, self._enqueue_sampling)
-            main.wait_event(self._photo_ready)
-            self._run("unwarp", self.buf, ("photo_u8",), self._enqueue_unwarp)
-            self.out_host.copy_(self.out_u8, non_blocking=True)
-            main.synchronize()
-        return self.out_host
+            ticket = self._submitted
+            self._submitted += 1
+            s = self._slots[ticket % 2]
+            with torch.cuda.stream(self._h2d):
+                if s["used"]:
+                    self._h2d.wait_event(s["ev_done"])             # the kernels of batch ticket-2 have read this slot's inputs
+                for k in self.SAMPLING_KEYS:
+                    s["buf"][k].copy_(h[k], non_blocking=True)
+                s["ev_in"].record()
+                s["buf"]["photo_u8"].copy_(h["photo_u8"], non_blocking=True)
+                s["ev_photo"].record()
+            main.wait_event(s["ev_in"])
+            if s["used"]:
+                main.wait_event(s["ev_out"])                       # the download of batch ticket-2 has read this slot's output
+            self._run("sampling", s["buf"], self.SAMPLING_KEYS, self._enqueue_sampling)
+            main.wait_event(s["ev_photo"])
+            self._run("unwarp", s["buf"], ("photo_u8", "out_u8"), self._enqueue_unwarp)
+            s["ev_done"].record(main)
+            with torch.cuda.stream(self._d2h):
+                self._d2h.wait_event(s["ev_done"])
+                s["out_host"].copy_(s["buf"]["out_u8"], non_blocking=True)
+                s["ev_out"].record()
+            s["used"] = True
+        return ticket
+
+    def wait(self, ticket: int) -> torch.Tensor:
+        """Block until the batch of `ticket` is on the host; the returned pinned tensor is reused by the second-next submit."""
+        s = self._slots[ticket % 2]
+        s["ev_out"].synchronize()
+        return s["out_host"]
+
+    def run_host(self, h: dict) -> torch.Tensor:
+        """Synchronous form: host inputs in, host uint8 image(s) out."""
+        return self.wait(self.submit_host(h))
 
     # ---- measurement helpers used by bench.py
     def profile_kernels(self, d: dict, iters: int = 5) -> dict:

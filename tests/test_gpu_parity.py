@@ -396,6 +396,42 @@ def test_two_chain_hypothesis_split_is_identical(dev, models, golden_dir):
     assert float(d.mean()) < FP32_MEAN and float(d.max()) < FP32_MAX, (float(d.mean()), float(d.max()))
 
 
+def test_pipeline_device_host_and_pipelined_submission_agree(dev, models):
+    """DewarpPipeline (the call bench.py times): CUDA-graph replay on device-resident inputs, the synchronous host call and the
+    double-buffered submit_host / wait form give the same uint8 images, equal to sampler + dewarp_fullres on the same inputs."""
+    from dvd_b200 import dewarp_fullres
+    from dvd_b200.pipeline import DewarpPipeline
+    H, W = 96, 128
+    pipe = DewarpPipeline(models["fp32"], diffusion_steps=3, n_batch=2, docs=1, height=H, width=W)
+    docs = [synth.make_doc_inputs(d, H=H, W=W) for d in (0, 1, 5, 0)]
+    hosts = []
+    for d in docs:
+        h = {k: d[k].contiguous().pin_memory() for k in ("y512", "mask_cat", "mask_y512", "line_msk", "x_T")}
+        h["photo_u8"] = d["photo"].permute(0, 2, 3, 1).to(torch.uint8).contiguous().pin_memory()
+        hosts.append(h)
+    want = []
+    for d, h in zip(docs, hosts):
+        m, _ = _sample(models["fp32"], d)
+        want.append(dewarp_fullres(m.to(dev), h["photo_u8"].to(dev)).cpu())
+    for h, w in zip(hosts, want):                                    # device-resident inputs, graph replay (twice: capture + replay)
+        dset = {k: v.to(dev) for k, v in h.items()}
+        for _ in range(2):
+            got = pipe.run_device(dset).cpu()
+            assert int((got.int() - w.int()).abs().max()) <= 1 and float((got != w).float().mean()) < 0.01
+    for h, w in zip(hosts, want):                                    # synchronous host call
+        assert torch.equal(pipe.run_host(h).clone(), pipe.run_host(h))
+        got = pipe.run_host(h)
+        assert int((got.int() - w.int()).abs().max()) <= 1 and float((got != w).float().mean()) < 0.01
+    tickets, outs = [], []
+    for i, h in enumerate(hosts):                                    # two batches outstanding
+        tickets.append(pipe.submit_host(h))
+        if i >= 1:
+            outs.append(pipe.wait(tickets[i - 1]).clone())
+    outs.append(pipe.wait(tickets[-1]).clone())
+    for got, h in zip(outs, hosts):
+        assert torch.equal(got, pipe.run_host(h))
+
+
 def test_seeded_noise_consumption_matches_reference_order(dev, models):
     """Without x_T the sampler draws randn(shape) then randn(n_batch, ...) like gaussian_diffusion.py:559-569."""
     inp = synth.make_doc_inputs(0, with_photo=False)
