@@ -284,7 +284,7 @@ def run_ours(a):
                 "e2e": {"value": e2e, "unit": "docs/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                         "p50_latency_ms": statistics.median(ms_e2e), "io": "uint8 HWC photo in, uint8 HWC dewarped image out",
                         "mode": "submit_host/wait, two batches outstanding (uploads and downloads overlap the kernels of the batch in between)",
-                        "synchronous_docs_per_s": a.docs * a.steps / (sum(ms_e2e) / 1e3)},
+                        "synchronous_docs_per_s": a.docs * a.steps * world / (sum(ms_e2e) / 1e3)},      # rank 0's clock x world
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "denoiser_tflops_effective": gflop / 1e3 / (tot_dev / a.steps / 1.0) if tot_dev > 0 else None,
