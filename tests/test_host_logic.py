@@ -142,3 +142,42 @@ def test_world_size_2_gloo_sharding_and_gather():
     assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
     assert res[0][2] == res[1][2] == list(range(7))        # every rank sees every document's timing
     assert abs(res[0][3] - res[1][3]) < 1e-12 and abs(res[0][3] - 0.16) < 1e-9     # max over ranks: 0.01*(1+3+5+7)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints ONE JSON line carrying the keys of the measurement
+    contract; no GPU, no compiled extension involved."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "docs/s" and d["value"] > 0 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_committed_bench_lines_carry_the_contract():
+    """profiles/r1_bench_lines.jsonl: every line of our arm has value / e2e / roofline / clocks / gpu_launches."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 0
+    for l in open(os.path.join(root, "profiles", "r1_bench_lines.jsonl")):
+        d = json.loads(l)
+        if d.get("impl") == "reference":
+            continue
+        n += 1
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config",
+                  "e2e", "gpu_launches", "clocks", "roofline"):
+            assert k in d, k
+        assert d["gpu_launches"] > 0 and d["warmup"] >= 3 and d["scaling"] == "weak"
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert n >= 5
