@@ -140,7 +140,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import synth
+    import synth_workload as synth
     torch.set_num_threads(os.cpu_count())
     sd = synth.make_state_dict(1234)
     inp = synth.make_doc_inputs(0, H=a.height, W=a.width)
@@ -165,7 +165,7 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(a):
     import torch.distributed as dist
-    from oracle import synth                                # synthetic workload generator only (no oracle compute here)
+    import synth_workload as synth                          # synthetic workload generator (no oracle code on this arm)
     import dvd_b200
     from dvd_b200 import _lib
     from dvd_b200.model import DiT
@@ -278,7 +278,7 @@ def run_ours(a):
                 "warmup": a.warmup, "ms_per_step": tot_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
                 "config": {"workload": workload_name(a), "docs_per_step_per_gpu": a.docs, "photo_hw": [a.height, a.width],
-                           "diffusion_steps": a.diffusion_steps, "n_batch": a.n_batch, "weights": "random-init (oracle/synth.py seed 1234)",
+                           "diffusion_steps": a.diffusion_steps, "n_batch": a.n_batch, "weights": "random-init (synth_workload.py seed 1234)",
                            "l2": "256 MiB flush write between timed iterations (value, synchronous e2e); pipelined e2e: no flush, every step streams new inputs and > 126 MB of weights", "cuda_graph": pipe.use_graph, "parallelism": f"document-sharded x{world}, no collective"},
                 "p50_latency_ms": statistics.median(ms_dev),
                 "e2e": {"value": e2e, "unit": "docs/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,

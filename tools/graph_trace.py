@@ -6,7 +6,7 @@ Usage: python tools/graph_trace.py [--docs 1] [--out gpurun_out/graph_trace.txt]
 import argparse, collections, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import synth                                   # synthetic workload generator only
+import synth_workload as synth                             # synthetic workload generator
 from dvd_b200.model import DiT
 from dvd_b200.pipeline import DewarpPipeline
 

@@ -6,7 +6,7 @@ UW_AMP sets the synthetic map's amplitude (0.05 = the strongly warped default of
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import synth
+import synth_workload as synth
 from dvd_b200 import dewarp_fullres
 
 
