@@ -68,3 +68,18 @@ def test_model_has_no_cpu_path():
         m(torch.zeros(2, 2, 64, 64), torch.tensor([666.0, 666.0]), y512=torch.zeros(2, 3, 512, 512), mask_cat=torch.zeros(2, 1, 512, 512),
           mask_y512=torch.zeros(2, 384, 64, 64), line_msk=torch.zeros(2, 64, 64, 64), init_flow=torch.zeros(2, 2, 64, 64),
           init_feat=torch.zeros(2, 256, 64, 64), tv=True, iter=True)
+
+
+def test_library_contains_blackwell_tensor_and_tma_instructions():
+    """The shipped library is the hand-written sm_100a path: its SASS holds tcgen05.mma (UTCHMMA), TMEM loads (LDTM) and TMA
+    loads / stores (UTMALDG / UTMASTG), and no legacy HMMA tensor instructions."""
+    import shutil, subprocess
+    from dvd_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
+        assert mnemonic in sass, mnemonic
+    assert " HMMA." not in sass and "HGMMA" not in sass
