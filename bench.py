@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DVD_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("DVD_PRECISION", "bf16x3"), choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--docs", type=int, default=1, help="documents per step per GPU")
     ap.add_argument("--height", type=int, default=1500)
     ap.add_argument("--width", type=int, default=2000)

@@ -13,13 +13,14 @@ LIB_PATH = os.path.join(_HERE, "libdvd_b200.so")
 
 PREC_FP32 = 0
 PREC_BF16 = 1
+PREC_BF16X3 = 2
 TABLE_ROW = 384 + 2304 + 3072
 
 _vp = C.c_void_p
 
 
 class Mat(C.Structure):
-    _fields_ = [("f32", _vp), ("bf16", _vp), ("n", C.c_int32), ("k", C.c_int32)]
+    _fields_ = [("f32", _vp), ("bf16", _vp), ("bf16_lo", _vp), ("n", C.c_int32), ("k", C.c_int32)]
 
 
 class DecLayer(C.Structure):
@@ -55,6 +56,7 @@ SIGNATURES = {
     "dvd_grid_sample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dvd_fullres_grid_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "dvd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "dvd_workspace_init": (_i, [_vp, _sz, _i, _i, _i, _vp]),
     "dvd_tables_init": (_i, [_WP, _FP, _i, _vp, _vp]),
     "dvd_static_forward": (_i, [_WP, _vp, _sz, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "dvd_denoise_step": (_i, [_WP, _vp, _sz, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _f, _f, _vp, _vp, _vp]),
@@ -64,7 +66,8 @@ SIGNATURES = {
     "dvd_workspace_tensor": (_vp, [_vp, _i, _i, _i, C.c_char_p, C.POINTER(C.c_longlong)]),
     "dvd_test_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "dvd_test_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
-    "dvd_gemm_bf16": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dvd_gemm_bf16": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "dvd_debug_stop_after": (_i, [_i]),
     "dvd_profile_begin": (_i, []),
     "dvd_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "dvd_launch_count": (C.c_longlong, [_i]),

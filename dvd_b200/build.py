@@ -22,7 +22,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 FLAGS += os.environ.get("DVD_NVCC_EXTRA", "").split()       # e.g. -DDVD_GEMM_TRACE for tools/gemm_trace.py (instrumented build)
-SOURCES = ["api.cu", "unwarp.cu", "gemm_simt.cu", "misc.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc3.cu", "attn_tc.cu", "denoiser.cu"]
+SOURCES = ["api.cu", "unwarp.cu", "gemm_simt.cu", "misc.cu", "gemm_tc.cu", "gemm_pair.cu", "attn_tc.cu", "denoiser.cu"]
 
 
 def _headers():

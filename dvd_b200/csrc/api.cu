@@ -62,8 +62,8 @@ extern "C" int dvd_check_device(void) {
   return 0;
 }
 
-// A[M,K] fp32, W[N,K] fp32 -> C[M,N] = A W^T + bias.  In bf16 mode the operands are first rounded
-// to bf16 into `scratch` (needs (M+N)*K*2 bytes) and the tcgen05 kernel is used.
+// A[M,K] fp32, W[N,K] fp32 -> C[M,N] = A W^T + bias.  In the tensor modes the operands are first converted into `scratch`
+// (bf16: (M+N)*K*2 bytes; bf16x3: twice that, plus 48 KB of split-K state when `splitk` != 0) and the tcgen05 kernels are used.
 extern "C" int dvd_test_gemm(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int precision,
                              void* scratch, size_t scratch_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -74,13 +74,32 @@ extern "C" int dvd_test_gemm(const float* A, const float* W, const float* bias, 
     p.e = e;
     return gemm_f32(p, A_DIRECT, B_NK, 1, st);
   }
-  size_t need = ((size_t)M + N) * K * 2 + 512;
-  DVD_REQUIRE(scratch && scratch_bytes >= need, "test_gemm: scratch needs %zu bytes", need);
-  __nv_bfloat16* A16 = (__nv_bfloat16*)scratch;
-  __nv_bfloat16* W16 = (__nv_bfloat16*)((char*)scratch + (((size_t)M * K * 2 + 255) & ~size_t(255)));
-  int rc = f32_to_bf16(A, A16, (long long)M * K, st); if (rc) return rc;
-  rc = f32_to_bf16(W, W16, (long long)N * K, st); if (rc) return rc;
-  return gemm_tc_bf16(A16, K, W16, K, M, N, K, e, st);
+  const bool x3 = precision == DVD_PREC_BF16X3;
+  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t a_b = al((size_t)M * K * 2), w_b = al((size_t)N * K * 2);
+  // optional split-K state behind the operands: 3 fp32 slices + 4096 counters (zeroed here, outside any timed region)
+  const size_t ops = (x3 ? 2 : 1) * (a_b + w_b);
+  const size_t sk_b = al((size_t)3 * M * N * 4) + 4096 * 4;
+  DVD_REQUIRE(scratch && scratch_bytes >= ops, "test_gemm: scratch needs %zu bytes", ops);
+  char* base = (char*)scratch;
+  TcMat a, w;
+  a.hi = (__nv_bfloat16*)base; w.hi = (__nv_bfloat16*)(base + a_b); a.ld = K; w.ld = K;
+  int rc;
+  if (x3) {
+    a.lo = (__nv_bfloat16*)(base + a_b + w_b); w.lo = (__nv_bfloat16*)(base + 2 * a_b + w_b);
+    rc = f32_split_bf16(A, (__nv_bfloat16*)a.hi, (__nv_bfloat16*)a.lo, (long long)M * K, st); if (rc) return rc;
+    rc = f32_split_bf16(W, (__nv_bfloat16*)w.hi, (__nv_bfloat16*)w.lo, (long long)N * K, st); if (rc) return rc;
+  } else {
+    rc = f32_to_bf16(A, (__nv_bfloat16*)a.hi, (long long)M * K, st); if (rc) return rc;
+    rc = f32_to_bf16(W, (__nv_bfloat16*)w.hi, (long long)N * K, st); if (rc) return rc;
+  }
+  TcScratch sk;
+  if (scratch_bytes >= ops + sk_b) {
+    sk.partial = (float*)(base + ops); sk.partial_floats = (size_t)3 * M * N;
+    sk.counters = (unsigned int*)(base + ops + al((size_t)3 * M * N * 4)); sk.n_counters = 4096;
+    DVD_CUDA(cudaMemsetAsync(sk.counters, 0, 4096 * 4, st));
+  }
+  return gemm_tc(a, w, M, N, K, e, sk.partial ? &sk : nullptr, st);
 }
 
 // q,k,v,o: [batch, T, heads*d] fp32.  fp32 mode: scratch holds the [batch*heads, T, T] scores.
@@ -107,21 +126,40 @@ extern "C" int dvd_test_attention(const float* q, const float* k, const float* v
     g.e.out = o; g.e.ldc = ld; g.sCn = (long long)T * ld; g.sCh = d;
     return gemm_f32(g, A_DIRECT, B_KN, batch * heads, st);
   }
+  // tensor modes: bf16 operands (DVD_PREC_BF16) or fp16 operands + split-pair output (DVD_PREC_BF16X3)
+  const bool x3 = precision == DVD_PREC_BF16X3;
   size_t n = (size_t)batch * T * ld;
-  DVD_REQUIRE(scratch_bytes >= n * 2 * 5, "test_attention: scratch needs %zu bytes", n * 10);
+  DVD_REQUIRE(scratch_bytes >= n * 2 * 6, "test_attention: scratch needs %zu bytes", n * 12);
   __nv_bfloat16* q16 = (__nv_bfloat16*)scratch; __nv_bfloat16* k16 = q16 + n; __nv_bfloat16* v16 = k16 + n; __nv_bfloat16* o16 = v16 + n;
-  __nv_bfloat16* vt16 = o16 + n;
-  int rc = f32_to_bf16(q, q16, n, st); if (rc) return rc;
-  rc = f32_to_bf16(k, k16, n, st); if (rc) return rc;
-  rc = f32_to_bf16(v, v16, n, st); if (rc) return rc;
-  rc = transpose_v_bf16(v16, ld, vt16, batch, T, ld, st); if (rc) return rc;
-  rc = attention_tc_bf16(q16, ld, k16, ld, vt16, o16, ld, batch, heads, T, d, scale, 1, st); if (rc) return rc;
-  return bf16_to_f32(o16, o, n, st);
+  __nv_bfloat16* vt16 = o16 + n; __nv_bfloat16* olo = vt16 + n;
+  int rc;
+  if (x3) {
+    rc = f32_to_f16(q, q16, n, st); if (rc) return rc;
+    rc = f32_to_f16(k, k16, n, st); if (rc) return rc;
+    rc = f32_to_f16(v, v16, n, st); if (rc) return rc;
+  } else {
+    rc = f32_to_bf16(q, q16, n, st); if (rc) return rc;
+    rc = f32_to_bf16(k, k16, n, st); if (rc) return rc;
+    rc = f32_to_bf16(v, v16, n, st); if (rc) return rc;
+  }
+  rc = transpose_v16(v16, ld, vt16, batch, T, ld, st); if (rc) return rc;
+  rc = attention_tc(q16, ld, k16, ld, vt16, o16, x3 ? olo : nullptr, ld, batch, heads, T, d, scale, 1, x3 ? 1 : 0, st); if (rc) return rc;
+  return pair_to_f32(o16, x3 ? olo : nullptr, o, n, st);
 }
 
-// Plain bf16 GEMM entry point (tuning / micro-benchmarks): out = A W^T + bias, bf16 output (and optional fp32 output).
-extern "C" int dvd_gemm_bf16(const void* A16, int lda, const void* W16, int ldw, const float* bias, void* out16, float* out32, int M, int N,
-                             int K, void* stream) {
+// Plain tensor-core GEMM entry point (tuning / micro-benchmarks): out = A W^T + bias, bf16 output (and optional fp32 output).
+// A16_lo / W16_lo non-null: split-precision pairs (three passes).  splitk_scratch (optional): >= 3*M*N*4 + 16 KB, zero-initialised.
+extern "C" int dvd_gemm_bf16(const void* A16, const void* A16_lo, int lda, const void* W16, const void* W16_lo, int ldw, const float* bias,
+                             void* out16, float* out32, int M, int N, int K, void* splitk_scratch, size_t splitk_bytes, void* stream) {
   Epilogue e; e.bias = bias; e.out_bf16 = (__nv_bfloat16*)out16; e.ldc_bf16 = N; e.out = out32; e.ldc = N;
-  return gemm_tc_bf16((const __nv_bfloat16*)A16, lda, (const __nv_bfloat16*)W16, ldw, M, N, K, e, (cudaStream_t)stream);
+  TcMat a, w;
+  a.hi = (const __nv_bfloat16*)A16; a.lo = (const __nv_bfloat16*)A16_lo; a.ld = lda;
+  w.hi = (const __nv_bfloat16*)W16; w.lo = (const __nv_bfloat16*)W16_lo; w.ld = ldw;
+  TcScratch sk;
+  const size_t need = (size_t)3 * M * N * 4 + 4096 * 4;
+  if (splitk_scratch && splitk_bytes >= need) {
+    sk.partial = (float*)splitk_scratch; sk.partial_floats = (size_t)3 * M * N;
+    sk.counters = (unsigned int*)((char*)splitk_scratch + (size_t)3 * M * N * 4); sk.n_counters = 4096;
+  }
+  return gemm_tc(a, w, M, N, K, e, sk.partial ? &sk : nullptr, (cudaStream_t)stream);
 }

@@ -14,6 +14,7 @@
 // d in {64, 256}; T a multiple of 128.
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 #include <string.h>
 
 namespace dvd {
@@ -56,10 +57,13 @@ constexpr int ACTX = 4;
 struct AttnCtx {
   CUtensorMap tmK[ACTX], tmVt[ACTX];
   __nv_bfloat16* out[ACTX];
+  __nv_bfloat16* out_lo[ACTX];     // low halves of the split output pair (DVD_PREC_BF16X3), or null
   int kv_div[ACTX];
 };
 
-template <int D>
+// F16: Q, K, V^T and P are IEEE fp16 instead of bf16 (DVD_PREC_BF16X3: 2^-12 operand rounding; measured on the oracle, fp16
+// attention inside an otherwise split-precision model moves the final map by 1.4e-6, bf16 attention by 1.1e-5)
+template <int D, bool F16>
 __global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ AttnCtx cx, int nsamp,
                                                       int ldo, int T, int heads, float scale_log2) {
   using Cfg = AttnCfg<D>;
@@ -89,6 +93,7 @@ __global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __g
   const CUtensorMap& tmK = cx.tmK[ctx];
   const CUtensorMap& tmVt = cx.tmVt[ctx];
   __nv_bfloat16* __restrict__ O = cx.out[ctx];
+  __nv_bfloat16* __restrict__ Olo = cx.out_lo[ctx];
 
   pdl_trigger();
   if (threadIdx.x == 0) {
@@ -130,8 +135,8 @@ __global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __g
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer
-      constexpr uint32_t idesc_qk = make_idesc_bf16(AQ, AKV);     // 128 x 64
-      constexpr uint32_t idesc_pv = make_idesc_bf16(AQ, D);       // 128 x D
+      constexpr uint32_t idesc_qk = F16 ? make_idesc_f16(AQ, AKV) : make_idesc_bf16(AQ, AKV);     // 128 x 64
+      constexpr uint32_t idesc_pv = F16 ? make_idesc_f16(AQ, D) : make_idesc_bf16(AQ, D);         // 128 x D
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       auto issue_qk = [&](int t) {
         const int s = t % ST, b = t % Cfg::NSB;
@@ -192,13 +197,19 @@ __global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __g
       const float alpha = (grow && t > 0) ? ex2(m - m_new) : 1.0f;
       if (grow) m = m_new;
       float sum = 0.f;
-      uint32_t pk[16];                                            // 32 bf16 probabilities
+      uint32_t pk[16];                                            // 32 16-bit probabilities
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
         const float a0 = ex2(fmaf(__uint_as_float(s0[j]), scale_log2, -m)), a1 = ex2(fmaf(__uint_as_float(s0[j + 1]), scale_log2, -m));
-        const __nv_bfloat162 pa = __floats2bfloat162_rn(a0, a1);
-        sum += __low2float(pa) + __high2float(pa);                // the sum uses the rounded values the tensor core multiplies with
-        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&pa);
+        if (F16) {
+          const __half2 pa = __floats2half2_rn(a0, a1);
+          sum += __low2float(pa) + __high2float(pa);              // the sum uses the rounded values the tensor core multiplies with
+          pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&pa);
+        } else {
+          const __nv_bfloat162 pa = __floats2bfloat162_rn(a0, a1);
+          sum += __low2float(pa) + __high2float(pa);
+          pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&pa);
+        }
       }
       l = l * alpha + sum;
       if (t > 0) {
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __g
     const float inv = 1.0f / (l + xch[(half ^ 1) * 128 + row]);
     mbar_wait(pv_done, (nt - 1) & 1);
     fence_after_sync();
-    __nv_bfloat16* orow = O + (size_t)(n * T + q0 + row) * ldo + h * D;
+    const size_t ooff = (size_t)(n * T + q0 + row) * ldo + h * D;
 #pragma unroll 1
     for (int c = half * (D / 2); c < (half + 1) * (D / 2); c += 32) {
       uint32_t o[32];
@@ -243,14 +254,13 @@ __global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __g
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
-        __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
-        __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
-        u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-        u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-        *reinterpret_cast<uint4*>(orow + c + j) = u;
+        uint4 u, l;
+        split_bf16x2(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv, u.x, l.x);
+        split_bf16x2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv, u.y, l.y);
+        split_bf16x2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv, u.z, l.z);
+        split_bf16x2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv, u.w, l.w);
+        *reinterpret_cast<uint4*>(O + ooff + c + j) = u;
+        if (Olo) *reinterpret_cast<uint4*>(Olo + ooff + c + j) = l;
       }
     }
   }
@@ -260,46 +270,43 @@ __global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __g
 }
 
 // V [nsamp, T, C] (row stride ldv) -> V^T [nsamp, C, T]; only used by the test hook (the denoiser's GEMM epilogue writes V^T directly)
-__global__ void k_transpose_v(const __nv_bfloat16* __restrict__ v, int ldv, __nv_bfloat16* __restrict__ vt, int T, int C) {
-  __shared__ __nv_bfloat16 tile[32][34];
+__global__ void k_transpose_v(const uint16_t* __restrict__ v, int ldv, uint16_t* __restrict__ vt, int T, int C) {
+  __shared__ uint16_t tile[32][34];
   const int n = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += 8) tile[r][threadIdx.x] = v[((size_t)n * T + t0 + r) * ldv + c0 + threadIdx.x];
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += 8) vt[((size_t)n * C + c0 + r) * T + t0 + threadIdx.x] = tile[threadIdx.x][r];
 }
-int transpose_v_bf16(const __nv_bfloat16* v, int ldv, __nv_bfloat16* vt, int nsamp, int T, int C, cudaStream_t st) {
+int transpose_v16(const void* v, int ldv, void* vt, int nsamp, int T, int C, cudaStream_t st) {
   DVD_REQUIRE(v && vt && T % 32 == 0 && C % 32 == 0, "transpose_v: bad args");
-  k_transpose_v<<<dim3(T / 32, C / 32, nsamp), dim3(32, 8), 0, st>>>(v, ldv, vt, T, C);
+  k_transpose_v<<<dim3(T / 32, C / 32, nsamp), dim3(32, 8), 0, st>>>((const uint16_t*)v, ldv, (uint16_t*)vt, T, C);
   DVD_LAUNCH_CHECK("k_transpose_v");
   return 0;
 }
 
-static int launch_attention(const CUtensorMap& tmQ, const AttnCtx& cx, int nctx, int ldo, int nsamp, int heads, int T, int d, float scale,
-                            cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DVD_CUDA(cudaFuncSetAttribute(k_attn_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::SMEM));
-    DVD_CUDA(cudaFuncSetAttribute(k_attn_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<256>::SMEM));
-    attr_set = true;
-  }
+template <int D, bool F16>
+static int launch_attention_t(const CUtensorMap& tmQ, const AttnCtx& cx, int nctx, int ldo, int nsamp, int heads, int T, float scale,
+                              cudaStream_t st) {
+  auto kern = k_attn_tc<D, F16>;
+  DVD_SET_MAX_SMEM(kern, AttnCfg<D>::SMEM);
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(T / AQ, heads, nsamp * nctx);
-  if (d == 64) DVD_CUDA(launch_pdl(2, k_attn_tc<64>, grid, dim3(ATHREADS), (size_t)AttnCfg<64>::SMEM, st, tmQ, cx, nsamp, ldo, T, heads, scale_log2));
-  else         DVD_CUDA(launch_pdl(2, k_attn_tc<256>, grid, dim3(ATHREADS), (size_t)AttnCfg<256>::SMEM, st, tmQ, cx, nsamp, ldo, T, heads, scale_log2));
+  DVD_CUDA(launch_pdl(2, kern, grid, dim3(ATHREADS), (size_t)AttnCfg<D>::SMEM, st, tmQ, cx, nsamp, ldo, T, heads, scale_log2));
   DVD_LAUNCH_CHECK("k_attn_tc");
   return 0;
 }
 
 // nctx (<= 4) key/value contexts attended by the SAME queries in one launch; k[i]/vt[i]/o[i]/kv_div[i] describe context i.
-int attention_tc_bf16_multi(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* const* k, int ldk, const __nv_bfloat16* const* vt,
-                            __nv_bfloat16* const* o, int ldo, const int* kv_div, int nctx, int nsamp, int heads, int T, int d, float scale,
-                            cudaStream_t st) {
+int attention_tc_multi(const void* q, int ldq, const void* const* k, int ldk, const void* const* vt, __nv_bfloat16* const* o,
+                       __nv_bfloat16* const* o_lo, int ldo, const int* kv_div, int nctx, int nsamp, int heads, int T, int d, float scale,
+                       int f16, cudaStream_t st) {
   DVD_REQUIRE(q && k && vt && o && kv_div && nctx >= 1 && nctx <= ACTX, "attention_tc_multi: bad arguments");
   DVD_REQUIRE((d == 64 || d == 256) && T % 128 == 0 && nsamp > 0, "attention_tc: bad shape d=%d T=%d", d, T);
   DVD_REQUIRE(ldo % 8 == 0 && (long long)nsamp * nctx <= 65535, "attention_tc: bad ldo / batch");
   CUtensorMap tmQ;
   AttnCtx cx;
   memset(&cx, 0, sizeof(cx));
+  // (fp16 and bf16 tiles are both plain 16-bit elements for TMA)
   int rc = make_tmap_bf16_2d(&tmQ, q, (uint64_t)nsamp * T, (uint64_t)heads * d, (uint64_t)ldq, AQ, 64); if (rc) return rc;
   for (int i = 0; i < nctx; ++i) {
     DVD_REQUIRE(k[i] && vt[i] && o[i] && kv_div[i] > 0 && nsamp % kv_div[i] == 0 && (reinterpret_cast<uintptr_t>(o[i]) & 15) == 0,
@@ -308,14 +315,20 @@ int attention_tc_bf16_multi(const __nv_bfloat16* q, int ldq, const __nv_bfloat16
     rc = make_tmap_bf16_2d(&cx.tmK[i], k[i], (uint64_t)nkv * T, (uint64_t)heads * d, (uint64_t)ldk, AKV, 64); if (rc) return rc;
     rc = make_tmap_bf16_2d(&cx.tmVt[i], vt[i], (uint64_t)nkv * heads * d, (uint64_t)T, (uint64_t)T, d, 64); if (rc) return rc;
     cx.out[i] = o[i]; cx.kv_div[i] = kv_div[i];
+    cx.out_lo[i] = o_lo ? o_lo[i] : nullptr;
+    DVD_REQUIRE((reinterpret_cast<uintptr_t>(cx.out_lo[i]) & 15) == 0, "attention_tc: o_lo must be 16-byte aligned");
   }
-  return launch_attention(tmQ, cx, nctx, ldo, nsamp, heads, T, d, scale, st);
+  if (d == 64) return f16 ? launch_attention_t<64, true>(tmQ, cx, nctx, ldo, nsamp, heads, T, scale, st)
+                          : launch_attention_t<64, false>(tmQ, cx, nctx, ldo, nsamp, heads, T, scale, st);
+  return f16 ? launch_attention_t<256, true>(tmQ, cx, nctx, ldo, nsamp, heads, T, scale, st)
+             : launch_attention_t<256, false>(tmQ, cx, nctx, ldo, nsamp, heads, T, scale, st);
 }
 
-int attention_tc_bf16(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt, __nv_bfloat16* o, int ldo,
-                      int nsamp, int heads, int T, int d, float scale, int kv_div, cudaStream_t st) {
+int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* vt, __nv_bfloat16* o, __nv_bfloat16* o_lo, int ldo, int nsamp,
+                 int heads, int T, int d, float scale, int kv_div, int f16, cudaStream_t st) {
   DVD_REQUIRE(q && k && vt && o, "attention_tc: null pointer");
-  return attention_tc_bf16_multi(q, ldq, &k, ldk, &vt, &o, ldo, &kv_div, 1, nsamp, heads, T, d, scale, st);
+  __nv_bfloat16* const* olo = o_lo ? &o_lo : nullptr;
+  return attention_tc_multi(q, ldq, &k, ldk, &vt, &o, olo, ldo, &kv_div, 1, nsamp, heads, T, d, scale, f16, st);
 }
 
 }  // namespace dvd

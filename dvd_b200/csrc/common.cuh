@@ -37,7 +37,19 @@ void count_launch(int n = 1);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-constexpr int kSMs = 148;            // B200: 2 dies x 74 SMs
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device): function attributes are per device
+// context, so a per-process flag would leave the second GPU of a process without the opt-in.
+#define DVD_SET_MAX_SMEM(kernel, bytes)                                                                   \
+  do {                                                                                                    \
+    static bool _set[64] = {};                                                                            \
+    int _dev = 0;                                                                                         \
+    DVD_CUDA(cudaGetDevice(&_dev));                                                                       \
+    if (_dev < 0 || _dev >= 64 || !_set[_dev]) {                                                          \
+      DVD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));  \
+      if (_dev >= 0 && _dev < 64) _set[_dev] = true;                                                      \
+    }                                                                                                     \
+  } while (0)
+
 constexpr int kTokens = 1024;        // 32 x 32 patches of the 64 x 64 map
 constexpr int kHid = 384;            // DiT-S hidden
 constexpr int kDec = 1536;           // decoder d_model

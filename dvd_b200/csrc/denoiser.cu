@@ -16,6 +16,11 @@
 
 namespace dvd {
 
+struct B16 { __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; };
+
+constexpr size_t kSplitKFloats = (size_t)12 << 20;      // 48 MB of fp32 split-K slices
+constexpr int kSplitKCounters = 4096;
+
 struct Workspace {
   // static, per document
   float *y4, *pyrP, *pyrQ, *feat, *a_stat, *ctx[3], *kv_static[3];
@@ -23,10 +28,13 @@ struct Workspace {
   float *a_r, *xe, *r, *qn, *q, *kv_r, *xo, *xs, *hmod, *qkv, *h1, *X, *pe, *hd, *qkv_d, *att_d, *f1, *f2, *S;
   float *flow[2], *xbuf[2], *pred;
   float* final_flow;                       // [docs * n_hyp, 2, 64, 64]: last pred_xstart of every hypothesis (input of the mean)
-  // bf16 operand staging (DVD_PREC_BF16)
-  __nv_bfloat16 *a_stat16, *ctx16[3], *a_r16, *r16, *qn16, *xo16, *hmod16, *h116, *hd16, *att_d16, *f116, *f216;
-  __nv_bfloat16 *q16, *kv_static16[3], *kv_r16, *qkv16, *qkv_d16;       // attention operands (Q, K row-major)
+  // 16-bit GEMM operand staging (tensor modes): plain bf16, or bf16 hi + lo pairs in DVD_PREC_BF16X3
+  B16 a_stat16, ctx16[3], a_r16, r16, qn16, xo16, hmod16, h116, hd16, att_d16, f116, f216;
+  // attention operands: bf16 (DVD_PREC_BF16) or fp16 (DVD_PREC_BF16X3)
+  __nv_bfloat16 *q16, *kv_static16[3], *kv_r16, *qkv16, *qkv_d16;       // Q, K row-major
   __nv_bfloat16 *vt_static16[3], *vt_r16, *vt_qkv16, *vt_d16;            // V^T [sample, C_v, 1024] written by the GEMM epilogues
+  TcScratch sk;                            // split-K slices + tile counters of the persistent GEMM
+  size_t counters_off;                     // byte offset of the counters (zeroed by dvd_workspace_init)
   size_t s_floats;
   size_t step_off;                         // offset of the per-step region
   size_t total_bytes;
@@ -39,10 +47,11 @@ struct Carver {
   char* take(size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return base ? base + o : nullptr; }
   float* F(size_t n) { return (float*)take(n * 4); }
   __nv_bfloat16* H(size_t n) { return (__nv_bfloat16*)take(n * 2); }
+  B16 P(size_t n, bool pair) { B16 b; b.hi = H(n); b.lo = pair ? H(n) : nullptr; return b; }
 };
 
 // per-document buffers (written by static_forward, read by every step of every hypothesis) + the gathered final flows
-static void carve_static(Carver& k, Workspace& w, int docs, int n_hyp, bool tc) {
+static void carve_static(Carver& k, Workspace& w, int docs, int n_hyp, bool tc, bool x3) {
   const size_t Md = (size_t)docs * 1024;
   w.y4 = k.F((size_t)docs * 512 * 512 * 4);
   w.pyrP = k.F((size_t)docs * 512 * 512 * 64);
@@ -53,15 +62,18 @@ static void carve_static(Carver& k, Workspace& w, int docs, int n_hyp, bool tc) 
   for (int i = 0; i < 3; ++i) w.kv_static[i] = k.F(Md * 768);
   w.final_flow = k.F((size_t)docs * n_hyp * 8192);
   if (tc) {
-    w.a_stat16 = k.H(Md * 1536);
-    for (int i = 0; i < 3; ++i) w.ctx16[i] = k.H(Md * 384);
+    w.a_stat16 = k.P(Md * 1536, x3);
+    for (int i = 0; i < 3; ++i) w.ctx16[i] = k.P(Md * 384, x3);
     for (int i = 0; i < 3; ++i) w.kv_static16[i] = k.H(Md * 768);
     for (int i = 0; i < 3; ++i) w.vt_static16[i] = k.H(Md * 384);
+    w.sk.partial = k.F(kSplitKFloats); w.sk.partial_floats = kSplitKFloats;
+    w.counters_off = k.off;
+    w.sk.counters = (unsigned int*)k.take(kSplitKCounters * sizeof(unsigned int)); w.sk.n_counters = kSplitKCounters;
   }
 }
 
 // per-step buffers of a group of docs * n_hyp samples
-static void carve_step(Carver& k, Workspace& w, int docs, int n_hyp, bool tc) {
+static void carve_step(Carver& k, Workspace& w, int docs, int n_hyp, bool tc, bool x3) {
   const size_t N = (size_t)docs * n_hyp, M = N * 1024;
   w.a_r = k.F(M * 1032);
   w.xe = k.F(M * 384); w.r = k.F(M * 384); w.qn = k.F(M * 384); w.q = k.F(M * 384);
@@ -79,43 +91,24 @@ static void carve_step(Carver& k, Workspace& w, int docs, int n_hyp, bool tc) {
   for (int i = 0; i < 2; ++i) { w.flow[i] = k.F(N * 8192); w.xbuf[i] = k.F(N * 8192); }
   w.pred = k.F(N * 8192);
   if (tc) {
-    w.a_r16 = k.H(M * 1032);
-    w.r16 = k.H(M * 384); w.qn16 = k.H(M * 384); w.xo16 = k.H(4 * M * 384); w.hmod16 = k.H(4 * M * 384);
-    w.h116 = k.H(4 * M * 1536); w.hd16 = k.H(M * 1536); w.att_d16 = k.H(M * 1536); w.f116 = k.H(M * 2048); w.f216 = k.H(M * 2048);
+    w.a_r16 = k.P(M * 1032, x3);
+    w.r16 = k.P(M * 384, x3); w.qn16 = k.P(M * 384, x3); w.xo16 = k.P(4 * M * 384, x3); w.hmod16 = k.P(4 * M * 384, x3);
+    w.h116 = k.P(4 * M * 1536, x3); w.hd16 = k.P(M * 1536, x3); w.att_d16 = k.P(M * 1536, x3); w.f116 = k.P(M * 2048, x3);
+    w.f216 = k.P(M * 2048, x3);
     w.q16 = k.H(M * 384); w.kv_r16 = k.H(M * 768); w.qkv16 = k.H(4 * M * 1152); w.qkv_d16 = k.H(M * 4608);
     w.vt_r16 = k.H(M * 384); w.vt_qkv16 = k.H(4 * M * 384); w.vt_d16 = k.H(M * 1536);
   }
 }
 
-// One document with >= 2 hypotheses may be sampled as two concurrent groups (dvd_sample): their per-step buffers are carved one after
-// the other in the same region, which must therefore be large enough for either layout.
-static bool can_split(int docs, int n_hyp) { return docs == 1 && n_hyp >= 2; }
-
 static Workspace carve(void* base, int docs, int n_hyp, int precision) {
   Workspace w{};
-  const bool tc = precision == DVD_PREC_BF16;
+  const bool tc = precision != DVD_PREC_FP32, x3 = precision == DVD_PREC_BF16X3;
   Carver k{(char*)base, 0};
-  carve_static(k, w, docs, n_hyp, tc);
+  carve_static(k, w, docs, n_hyp, tc, x3);
   w.step_off = k.off;
-  carve_step(k, w, docs, n_hyp, tc);
+  carve_step(k, w, docs, n_hyp, tc, x3);
   w.total_bytes = k.off;
-  if (can_split(docs, n_hyp)) {
-    Carver k2{nullptr, w.step_off};
-    Workspace t{};
-    carve_step(k2, t, 1, n_hyp / 2, tc);
-    carve_step(k2, t, 1, n_hyp - n_hyp / 2, tc);
-    if (k2.off > w.total_bytes) w.total_bytes = k2.off;
-  }
   return w;
-}
-
-// per-step buffers of one hypothesis group, carved at `off` (updated) of the same workspace; static buffers shared with `master`
-static Workspace carve_group(const Workspace& master, void* base, size_t& off, int n_hyp_g, bool tc) {
-  Workspace g = master;
-  Carver k{(char*)base, off};
-  carve_step(k, g, 1, n_hyp_g, tc);
-  off = k.off;
-  return g;
 }
 
 // ------------------------------------------------------------------------------------------ fp32 attention (GEMM + softmax + GEMM)
@@ -179,16 +172,26 @@ struct Ctx {
   Workspace ws;
   int docs, n_hyp, prec;
   cudaStream_t st;
-  bool tc() const { return prec == DVD_PREC_BF16; }
+  bool tc() const { return prec != DVD_PREC_FP32; }
+  bool x3() const { return prec == DVD_PREC_BF16X3; }
 };
 
+// 16-bit destinations of an epilogue: the operand of the next GEMM (plain bf16 or split pair) ...
+static void out_operand(Epilogue& e, const B16& dst, int ld) { e.out_bf16 = dst.hi; e.out_lo = dst.lo; e.ldc_bf16 = ld; }
+// ... or an operand of the attention kernel (bf16, fp16 in the split-precision mode)
+static void out_attn(const Ctx& c, Epilogue& e, __nv_bfloat16* dst, int ld) { e.out_bf16 = dst; e.out_lo = nullptr; e.ldc_bf16 = ld; e.out_f16 = c.x3() ? 1 : 0; }
+
 // C = epi(A * W[row0 : row0+N, :]^T)
-static int linear(const Ctx& c, const float* A32, const __nv_bfloat16* A16, int lda, const dvd_mat_t& W, int row0, int M, int N,
+static int linear(const Ctx& c, const float* A32, const B16& A16, int lda, const dvd_mat_t& W, int row0, int M, int N,
                   const Epilogue& e) {
   ProfScope ps(PC_GEMM, c.st, 2.0 * M * N * W.k);
   if (c.tc()) {
-    DVD_REQUIRE(A16 && W.bf16, "linear: bf16 operands missing");
-    return gemm_tc_bf16(A16, lda, (const __nv_bfloat16*)W.bf16 + (size_t)row0 * W.k, W.k, M, N, W.k, e, c.st);
+    DVD_REQUIRE(A16.hi && W.bf16 && (!c.x3() || (A16.lo && W.bf16_lo)), "linear: 16-bit operands missing");
+    TcMat a, w;
+    a.hi = A16.hi; a.lo = c.x3() ? A16.lo : nullptr; a.ld = lda;
+    w.hi = (const __nv_bfloat16*)W.bf16 + (size_t)row0 * W.k; w.ld = W.k;
+    w.lo = c.x3() ? (const __nv_bfloat16*)W.bf16_lo + (size_t)row0 * W.k : nullptr;
+    return gemm_tc(a, w, M, N, W.k, e, &c.ws.sk, c.st);
   }
   GemmParams p = linear_params(A32, lda, W.f32 + (size_t)row0 * W.k, M, N, W.k);
   p.e = e;
@@ -207,39 +210,52 @@ static int conv3x3(const Ctx& c, const float* in, float* out, int B, int H, int 
   return gemm_f32(p, A_CONV3, B_NK, 1, c.st);
 }
 
+static TcMat weight_op(const Ctx& c, const dvd_mat_t& W) {
+  TcMat w;
+  w.hi = (const __nv_bfloat16*)W.bf16; w.lo = c.x3() ? (const __nv_bfloat16*)W.bf16_lo : nullptr; w.ld = W.k;
+  return w;
+}
+
 static int static_forward(const Ctx& c, const float* y512, const float* mask_cat, const float* mask_y512, const float* line_msk) {
   const dvd_weights_t& w = *c.w; const Workspace& s = c.ws; cudaStream_t st = c.st;
   const int B = c.docs, Md = B * 1024;
+  const bool tc = c.tc(), x3 = c.x3();
   // ---- K1 pyramid (CM:83-95): 7 x conv3x3+ReLU, 3 x maxpool, NHWC
   DVD_TRY(pack_y4(y512, mask_cat, s.y4, B, st));
-  if (c.tc()) {
-    // level_0 (Cin = 4): the 3x3x4 patch of every pixel is written once as a K = 64 (36 valid + zero padding) bf16 row
+  if (tc) {
+    // level_0 (Cin = 4): the 3x3x4 patch of every pixel is written once as a K = 64 (36 valid + zero padding) 16-bit row
     // (im2col, 128 B per pixel) and multiplied by the K-padded weight on tcgen05; the six wide convs run as implicit GEMMs
     // directly on the NHWC activations; the last pool writes the fp32 feature map the rest of the model consumes.
-    __nv_bfloat16 *P = (__nv_bfloat16*)s.pyrP, *Q = (__nv_bfloat16*)s.pyrQ;
+    // pyrP / pyrQ are fp32-sized: the first half holds the bf16 activation, the second half its low part (split-precision mode).
+    const size_t half = (size_t)B * 512 * 512 * 64;
+    B16 P, Q;
+    P.hi = (__nv_bfloat16*)s.pyrP; P.lo = x3 ? P.hi + half : nullptr;
+    Q.hi = (__nv_bfloat16*)s.pyrQ; Q.lo = x3 ? Q.hi + half : nullptr;
+    auto op = [&](const B16& b) { TcMat m; m.hi = b.hi; m.lo = b.lo; m.ld = 64; return m; };
     {
       ProfScope ps(PC_CONV, st, 2.0 * B * 512 * 512 * 64 * 36.0);
-      DVD_REQUIRE(w.pyr[0].bf16, "pyramid level_0 bf16 (K-padded) weight missing");
-      DVD_TRY(im2col3x3_c4_bf16(s.y4, Q, B, 512, 512, st));                       // Q: [B*512*512, 64] bf16
-      Epilogue e; e.bias = w.pyr_b[0]; e.act = ACT_RELU; e.out_bf16 = P; e.ldc_bf16 = 64;
-      DVD_TRY(gemm_tc_bf16(Q, 64, (const __nv_bfloat16*)w.pyr[0].bf16, 64, B * 512 * 512, 64, 64, e, st));
+      DVD_REQUIRE(w.pyr[0].bf16 && (!x3 || w.pyr[0].bf16_lo), "pyramid level_0 16-bit (K-padded) weight missing");
+      DVD_TRY(im2col3x3_c4_bf16(s.y4, Q.hi, Q.lo, B, 512, 512, st));                  // Q: [B*512*512, 64]
+      Epilogue e; e.bias = w.pyr_b[0]; e.act = ACT_RELU; out_operand(e, P, 64);
+      TcMat wt = weight_op(c, w.pyr[0]); wt.ld = 64;
+      DVD_TRY(gemm_tc(op(Q), wt, B * 512 * 512, 64, 64, e, nullptr, st));
     }
-    auto conv = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int H, int Cin, int layer) -> int {
+    auto conv = [&](const B16& in, const B16& out, int H, int Cin, int layer) -> int {
       const int Cout = w.pyr[layer].n;
       ProfScope ps(PC_CONV, st, 2.0 * B * H * H * Cout * 9.0 * Cin);
-      Epilogue e; e.bias = w.pyr_b[layer]; e.act = ACT_RELU; e.out_bf16 = out; e.ldc_bf16 = Cout;
-      DVD_REQUIRE(w.pyr[layer].bf16, "pyramid bf16 weights missing");
-      return conv3x3_tc_bf16(in, (const __nv_bfloat16*)w.pyr[layer].bf16, B, H, H, Cin, Cout, e, st);
+      Epilogue e; e.bias = w.pyr_b[layer]; e.act = ACT_RELU; out_operand(e, out, Cout);
+      DVD_REQUIRE(w.pyr[layer].bf16 && (!x3 || w.pyr[layer].bf16_lo), "pyramid 16-bit weights missing");
+      return conv3x3_tc(op(in), weight_op(c, w.pyr[layer]), B, H, H, Cin, Cout, e, st);
     };
     DVD_TRY(conv(P, Q, 512, 64, 1));
-    DVD_TRY(maxpool2_nhwc_bf16(Q, P, nullptr, B, 512, 512, 64, st));
+    DVD_TRY(maxpool2_nhwc_bf16(Q.hi, Q.lo, P.hi, P.lo, nullptr, B, 512, 512, 64, st));
     DVD_TRY(conv(P, Q, 256, 64, 2));
     DVD_TRY(conv(Q, P, 256, 128, 3));
-    DVD_TRY(maxpool2_nhwc_bf16(P, Q, nullptr, B, 256, 256, 128, st));
+    DVD_TRY(maxpool2_nhwc_bf16(P.hi, P.lo, Q.hi, Q.lo, nullptr, B, 256, 256, 128, st));
     DVD_TRY(conv(Q, P, 128, 128, 4));
     DVD_TRY(conv(P, Q, 128, 256, 5));
     DVD_TRY(conv(Q, P, 128, 256, 6));
-    DVD_TRY(maxpool2_nhwc_bf16(P, nullptr, s.feat, B, 128, 128, 256, st));
+    DVD_TRY(maxpool2_nhwc_bf16(P.hi, P.lo, nullptr, nullptr, s.feat, B, 128, 128, 256, st));
   } else {
     DVD_TRY(conv3x3(c, s.y4, s.pyrP, B, 512, 512, 4, w.pyr[0], w.pyr_b[0]));
     DVD_TRY(conv3x3(c, s.pyrP, s.pyrQ, B, 512, 512, 64, w.pyr[1], w.pyr_b[1]));
@@ -257,27 +273,30 @@ static int static_forward(const Ctx& c, const float* y512, const float* mask_cat
   for (int i = 0; i < 3; ++i) {
     const int emb = 2 + i;                       // emb[] order: obs, r, c, m, l
     const int C = i == 0 ? 256 : (i == 1 ? 384 : 64);
-    if (i == 0) DVD_TRY(patchify_nhwc(s.feat, c.tc() ? nullptr : s.a_stat, c.tc() ? s.a_stat16 : nullptr, 4 * C, B, C, st));
-    else DVD_TRY(patchify_nchw(i == 1 ? mask_y512 : line_msk, c.tc() ? nullptr : s.a_stat, c.tc() ? s.a_stat16 : nullptr, 4 * C, B, C, st));
-    Epilogue ee = e; ee.bias = w.emb_b[emb]; ee.out = c.tc() ? nullptr : s.ctx[i]; ee.ldc = 384;
-    ee.out_bf16 = c.tc() ? s.ctx16[i] : nullptr; ee.ldc_bf16 = 384;
+    if (i == 0) DVD_TRY(patchify_nhwc(s.feat, tc ? nullptr : s.a_stat, s.a_stat16.hi, s.a_stat16.lo, 4 * C, B, C, st));
+    else DVD_TRY(patchify_nchw(i == 1 ? mask_y512 : line_msk, tc ? nullptr : s.a_stat, s.a_stat16.hi, s.a_stat16.lo, 4 * C, B, C, st));
+    Epilogue ee = e; ee.bias = w.emb_b[emb]; ee.out = tc ? nullptr : s.ctx[i]; ee.ldc = 384;
+    if (tc) out_operand(ee, s.ctx16[i], 384);
     DVD_TRY(linear(c, s.a_stat, s.a_stat16, 4 * C, w.emb[emb], 0, Md, 384, ee));
     // ---- static cross-attention K,V (in_proj rows 384..1151)
-    Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = c.tc() ? nullptr : s.kv_static[i]; ek.ldc = 768;
-    ek.out_bf16 = c.tc() ? s.kv_static16[i] : nullptr; ek.ldc_bf16 = 768;
-    if (c.tc()) { ek.vt_out = s.vt_static16[i]; ek.vt_col0 = 384; }
+    Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = tc ? nullptr : s.kv_static[i]; ek.ldc = 768;
+    if (tc) { out_attn(c, ek, s.kv_static16[i], 768); ek.vt_out = s.vt_static16[i]; ek.vt_col0 = 384; }
     DVD_TRY(linear(c, s.ctx[i], s.ctx16[i], 384, w.xattn_in, 384, Md, 768, ek));
   }
   return 0;
 }
 
 static int attention(const Ctx& c, const float* q, const __nv_bfloat16* q16, int ldq, const float* k, const __nv_bfloat16* k16, int ldk,
-                     const float* v, const __nv_bfloat16* vt16, int ldv, float* o, __nv_bfloat16* o16, int ldo, int nsamp, int d,
+                     const float* v, const __nv_bfloat16* vt16, int ldv, float* o, const B16& o16, int ldo, int nsamp, int d,
                      float scale, int kv_div) {
   ProfScope ps(PC_ATTN, c.st, 4.0 * nsamp * kHeads * 1024.0 * 1024.0 * d);
-  if (c.tc()) return attention_tc_bf16(q16, ldq, k16, ldk, vt16, o16, ldo, nsamp, kHeads, 1024, d, scale, kv_div, c.st);
+  if (c.tc()) return attention_tc(q16, ldq, k16, ldk, vt16, o16.hi, o16.lo, ldo, nsamp, kHeads, 1024, d, scale, kv_div, c.x3() ? 1 : 0, c.st);
   return attention_f32(q, ldq, k, ldk, v, ldv, o, ldo, nsamp, kHeads, 1024, d, scale, kv_div, c.ws.S, c.ws.s_floats, c.st);
 }
+
+// test hook (dvd_debug_stop_after): leave denoise_step after a stage so that the stage's output can be read from the workspace
+//   1 = after the DiT block ("X" = x1|x2|x3|x4), 2 = after the adaptive positional encoding, 3 + l = after decoder layer l
+static thread_local int g_stop_after = 0;
 
 static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, const float* init_feat_nchw, int init_feat_div,
                         int feat_mode, const float* trow, float da, float db, float* pred, float* x_prev) {
@@ -286,37 +305,40 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
   const bool tc = c.tc();
   const float* ada = trow + 384;                 // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
   const float* fin = trow + 384 + 2304;          // shift[1536], scale[1536]
+  auto off16 = [](const B16& b, size_t n) { B16 r; r.hi = b.hi + n; r.lo = b.lo ? b.lo + n : nullptr; return r; };
   // ---- obs embed (CM:571) and r embed (CM:602-603) with the fused feature warp (GD:618-624)
   DVD_TRY(obs_embed(x_t, w.emb[0].f32, w.emb_b[0], w.pos, s.xe, N, st));
   const int lda_r = 1032;                       // 258*4; TMA zero-fills the K tail of the last 64-wide box
-  DVD_TRY(build_r_operand(init_flow, s.feat, init_feat_nchw, init_feat_div, feat_mode, tc ? nullptr : s.a_r, tc ? s.a_r16 : nullptr,
+  DVD_TRY(build_r_operand(init_flow, s.feat, init_feat_nchw, init_feat_div, feat_mode, tc ? nullptr : s.a_r, s.a_r16.hi, s.a_r16.lo,
                           lda_r, N, c.n_hyp, st));
   {
     Epilogue e; e.bias = w.emb_b[1]; e.pos = w.pos; e.pos_rows = 1024; e.out = tc ? nullptr : s.r; e.ldc = 384;
-    e.out_bf16 = tc ? s.r16 : nullptr; e.ldc_bf16 = 384;
+    if (tc) out_operand(e, s.r16, 384);
     DVD_TRY(linear(c, s.a_r, s.a_r16, lda_r, w.emb[1], 0, M, 384, e));
   }
   // ---- cross attention (CM:237-265): one shared query, four contexts
-  DVD_TRY(layernorm(s.xe, 384, tc ? nullptr : s.qn, 384, tc ? s.qn16 : nullptr, 384, M, 384, 1e-6f, nullptr, nullptr, nullptr, nullptr, st));
+  DVD_TRY(layernorm(s.xe, 384, tc ? nullptr : s.qn, 384, s.qn16.hi, s.qn16.lo, 384, M, 384, 1e-6f, nullptr, nullptr, nullptr, nullptr, st));
   {
-    Epilogue e; e.bias = w.xattn_in_b; e.out = tc ? nullptr : s.q; e.ldc = 384; e.out_bf16 = tc ? s.q16 : nullptr; e.ldc_bf16 = 384;
+    Epilogue e; e.bias = w.xattn_in_b; e.out = tc ? nullptr : s.q; e.ldc = 384;
+    if (tc) out_attn(c, e, s.q16, 384);
     DVD_TRY(linear(c, s.qn, s.qn16, 384, w.xattn_in, 0, M, 384, e));
-    Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = tc ? nullptr : s.kv_r; ek.ldc = 768; ek.out_bf16 = tc ? s.kv_r16 : nullptr; ek.ldc_bf16 = 768;
-    if (tc) { ek.vt_out = s.vt_r16; ek.vt_col0 = 384; }
+    Epilogue ek; ek.bias = w.xattn_in_b + 384; ek.out = tc ? nullptr : s.kv_r; ek.ldc = 768;
+    if (tc) { out_attn(c, ek, s.kv_r16, 768); ek.vt_out = s.vt_r16; ek.vt_col0 = 384; }
     DVD_TRY(linear(c, s.r, s.r16, 384, w.xattn_in, 384, M, 768, ek));
   }
   if (tc) {
     // the four contexts (stream order x1..x4 = cond, msk6, msk_line, r; CM:243-265) share the queries: ONE launch of 4 x N x 6 x 8 CTAs
     ProfScope ps(PC_ATTN, st, 4.0 * 4.0 * N * kHeads * 1024.0 * 1024.0 * 64);
-    const __nv_bfloat16* kk[4] = {s.kv_static16[0], s.kv_static16[1], s.kv_static16[2], s.kv_r16};
-    const __nv_bfloat16* vv[4] = {s.vt_static16[0], s.vt_static16[1], s.vt_static16[2], s.vt_r16};
-    __nv_bfloat16* oo[4] = {s.xo16, s.xo16 + (size_t)M * 384, s.xo16 + (size_t)2 * M * 384, s.xo16 + (size_t)3 * M * 384};
+    const void* kk[4] = {s.kv_static16[0], s.kv_static16[1], s.kv_static16[2], s.kv_r16};
+    const void* vv[4] = {s.vt_static16[0], s.vt_static16[1], s.vt_static16[2], s.vt_r16};
+    __nv_bfloat16* oo[4]; __nv_bfloat16* ol[4];
+    for (int i = 0; i < 4; ++i) { oo[i] = s.xo16.hi + (size_t)i * M * 384; ol[i] = s.xo16.lo ? s.xo16.lo + (size_t)i * M * 384 : nullptr; }
     const int dv[4] = {c.n_hyp, c.n_hyp, c.n_hyp, 1};
-    DVD_TRY(attention_tc_bf16_multi(s.q16, 384, kk, 768, vv, oo, 384, dv, 4, N, kHeads, 1024, 64, 0.125f, st));
+    DVD_TRY(attention_tc_multi(s.q16, 384, kk, 768, vv, oo, s.xo16.lo ? ol : nullptr, 384, dv, 4, N, kHeads, 1024, 64, 0.125f, c.x3() ? 1 : 0, st));
   } else {
     for (int i = 0; i < 4; ++i) {                // stream order x1..x4 = cond, msk6, msk_line, r  (CM:243-265)
       const float* kv = i < 3 ? s.kv_static[i] : s.kv_r;
-      DVD_TRY(attention(c, s.q, nullptr, 384, kv, nullptr, 768, kv + 384, nullptr, 768, s.xo + (size_t)i * M * 384, nullptr, 384, N, 64,
+      DVD_TRY(attention(c, s.q, nullptr, 384, kv, nullptr, 768, kv + 384, nullptr, 768, s.xo + (size_t)i * M * 384, B16(), 384, N, 64,
                         0.125f, i < 3 ? c.n_hyp : 1));
     }
   }
@@ -325,11 +347,11 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     DVD_TRY(linear(c, s.xo, s.xo16, 384, w.xattn_out, 0, 4 * M, 384, e));
   }
   // ---- adaLN self-attention on the 4 streams (CM:268-292), shared weights
-  DVD_TRY(layernorm(s.xs, 384, tc ? nullptr : s.hmod, 384, tc ? s.hmod16 : nullptr, 384, 4 * M, 384, 1e-6f, nullptr, nullptr, ada + 0,
+  DVD_TRY(layernorm(s.xs, 384, tc ? nullptr : s.hmod, 384, s.hmod16.hi, s.hmod16.lo, 384, 4 * M, 384, 1e-6f, nullptr, nullptr, ada + 0,
                     ada + 384, st));
   {
-    Epilogue e; e.bias = w.blk_qkv_b; e.out = s.qkv; e.ldc = 1152; e.out_bf16 = tc ? s.qkv16 : nullptr; e.ldc_bf16 = 1152;
-    if (tc) { e.out = nullptr; e.vt_out = s.vt_qkv16; e.vt_col0 = 768; }
+    Epilogue e; e.bias = w.blk_qkv_b; e.out = tc ? nullptr : s.qkv; e.ldc = 1152;
+    if (tc) { out_attn(c, e, s.qkv16, 1152); e.vt_out = s.vt_qkv16; e.vt_col0 = 768; }
     DVD_TRY(linear(c, s.hmod, s.hmod16, 384, w.blk_qkv, 0, 4 * M, 1152, e));
   }
   DVD_TRY(attention(c, s.qkv, s.qkv16, 1152, s.qkv + 384, tc ? s.qkv16 + 384 : nullptr, 1152, s.qkv + 768, s.vt_qkv16, 1152,
@@ -339,16 +361,17 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     DVD_TRY(linear(c, s.xo, s.xo16, 384, w.blk_proj, 0, 4 * M, 384, e));
   }
   // ---- adaLN MLP; fc2 writes straight into the concatenated decoder input (CM:623)
-  DVD_TRY(layernorm(s.xs, 384, tc ? nullptr : s.hmod, 384, tc ? s.hmod16 : nullptr, 384, 4 * M, 384, 1e-6f, nullptr, nullptr, ada + 1152,
+  DVD_TRY(layernorm(s.xs, 384, tc ? nullptr : s.hmod, 384, s.hmod16.hi, s.hmod16.lo, 384, 4 * M, 384, 1e-6f, nullptr, nullptr, ada + 1152,
                     ada + 1536, st));
   {
-    Epilogue e; e.bias = w.blk_fc1_b; e.act = ACT_GELU; e.out = tc ? nullptr : s.h1; e.ldc = 1536;
-    e.out_bf16 = tc ? s.h116 : nullptr; e.ldc_bf16 = 1536;
+    Epilogue e; e.bias = w.blk_fc1_b; e.act = c.x3() ? ACT_GELU_EXACT : ACT_GELU; e.out = tc ? nullptr : s.h1; e.ldc = 1536;
+    if (tc) out_operand(e, s.h116, 1536);
     DVD_TRY(linear(c, s.hmod, s.hmod16, 384, w.blk_fc1, 0, 4 * M, 1536, e));
     Epilogue f; f.bias = w.blk_fc2_b; f.gate = ada + 1920; f.resid = s.xs; f.ldr = 384; f.out = s.X; f.ldc = 1536;
     f.group_rows = M; f.group_col_stride = 384;
     DVD_TRY(linear(c, s.h1, s.h116, 1536, w.blk_fc2, 0, 4 * M, 384, f));
   }
+  if (g_stop_after == 1) return 0;
   // ---- decoder: adaptive 2-D positional encoding (CA:143-157)
   {
     float* mean = s.pe; float* hs1 = s.pe + (size_t)N * 1536 * 33; float* hs = hs1 + (size_t)N * 1536;
@@ -359,13 +382,14 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     DVD_TRY(gemv_pair(hs1, ws1, 1536, w.h_scale2.f32, w.w_scale2.f32, w.h_scale2_b, w.w_scale2_b, hs, wsv, 1536, N, 1536, 1536, 3, st));
     DVD_TRY(posenc_add(s.X, hs, wsv, w.dec_hpe, w.dec_wpe, N, 1536, st));
   }
+  if (g_stop_after == 2) return 0;
   // ---- 6 decoder layers (CA:377-396)
   for (int l = 0; l < 6; ++l) {
     const dvd_dec_layer_t& L = w.dec[l];
-    DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, tc ? s.hd16 : nullptr, 1536, M, 1536, 1e-5f, L.n1_w, L.n1_b, nullptr, nullptr, st));
+    DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n1_w, L.n1_b, nullptr, nullptr, st));
     {
-      Epilogue e; e.out = tc ? nullptr : s.qkv_d; e.ldc = 4608; e.out_bf16 = tc ? s.qkv_d16 : nullptr; e.ldc_bf16 = 4608;
-      if (tc) { e.vt_out = s.vt_d16; e.vt_col0 = 3072; }
+      Epilogue e; e.out = tc ? nullptr : s.qkv_d; e.ldc = 4608;
+      if (tc) { out_attn(c, e, s.qkv_d16, 4608); e.vt_out = s.vt_d16; e.vt_col0 = 3072; }
       DVD_TRY(linear(c, s.hd, s.hd16, 1536, L.qkv, 0, M, 4608, e));
     }
     DVD_TRY(attention(c, s.qkv_d, s.qkv_d16, 4608, s.qkv_d + 1536, tc ? s.qkv_d16 + 1536 : nullptr, 4608, s.qkv_d + 3072, s.vt_d16, 4608,
@@ -374,28 +398,30 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
       Epilogue e; e.resid = s.X; e.ldr = 1536; e.out = s.X; e.ldc = 1536;
       DVD_TRY(linear(c, s.att_d, s.att_d16, 1536, L.fc, 0, M, 1536, e));
     }
-    DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, tc ? s.hd16 : nullptr, 1536, M, 1536, 1e-5f, L.n2_w, L.n2_b, nullptr, nullptr, st));
+    DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n2_w, L.n2_b, nullptr, nullptr, st));
     {
       Epilogue e; e.scale = L.bn1_scale; e.shift = L.bn1_shift; e.act = ACT_RELU; e.out = tc ? nullptr : s.f1; e.ldc = 2048;
-      e.out_bf16 = tc ? s.f116 : nullptr; e.ldc_bf16 = 2048;
+      if (tc) out_operand(e, s.f116, 2048);
       DVD_TRY(linear(c, s.hd, s.hd16, 1536, L.conv1, 0, M, 2048, e));
     }
-    if (tc) DVD_TRY(dwconv3x3_bn_relu_bf16(s.f116, L.dw_w, L.bn2_scale, L.bn2_shift, s.f216, N, 2048, st));
+    if (tc) DVD_TRY(dwconv3x3_bn_relu_bf16(s.f116.hi, s.f116.lo, L.dw_w, L.bn2_scale, L.bn2_shift, s.f216.hi, s.f216.lo, N, 2048, st));
     else DVD_TRY(dwconv3x3_bn_relu(s.f1, L.dw_w, L.bn2_scale, L.bn2_shift, s.f2, nullptr, N, 2048, st));
     {
       Epilogue e; e.scale = L.bn3_scale; e.shift = L.bn3_shift; e.act = ACT_RELU; e.resid = s.X; e.ldr = 1536; e.out = s.X; e.ldc = 1536;
       DVD_TRY(linear(c, s.f2, s.f216, 2048, L.conv2, 0, M, 1536, e));
     }
+    if (g_stop_after == 3 + l) return 0;
   }
   // ---- final layer + unpatchify + init_flow + DDIM update (one kernel)
   DVD_TRY(final_layer(s.X, w.dec_ln_w, w.dec_ln_b, fin, fin + 1536, w.fin.f32, w.fin_b, init_flow, x_t, da, db, pred, x_prev, N, st));
+  (void)off16;
   return 0;
 }
 
 static int make_ctx(Ctx& c, const dvd_weights_t* w, void* workspace, size_t bytes, int docs, int n_hyp, int precision, void* stream) {
   DVD_REQUIRE(w && workspace, "null weights/workspace");
   DVD_REQUIRE(docs > 0 && n_hyp > 0, "docs and n_hyp must be positive");
-  DVD_REQUIRE(precision == DVD_PREC_FP32 || precision == DVD_PREC_BF16, "bad precision %d", precision);
+  DVD_REQUIRE(precision == DVD_PREC_FP32 || precision == DVD_PREC_BF16 || precision == DVD_PREC_BF16X3, "bad precision %d", precision);
   DVD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   c.w = w; c.docs = docs; c.n_hyp = n_hyp; c.prec = precision; c.st = (cudaStream_t)stream;
   c.ws = carve(workspace, docs, n_hyp, precision);
@@ -413,6 +439,15 @@ using namespace dvd;
 extern "C" size_t dvd_workspace_bytes(int docs, int n_hyp, int precision) {
   if (docs <= 0 || n_hyp <= 0) return 0;
   return carve(nullptr, docs, n_hyp, precision).total_bytes;
+}
+
+extern "C" int dvd_workspace_init(void* workspace, size_t workspace_bytes, int docs, int n_hyp, int precision, void* stream) {
+  DVD_REQUIRE(workspace && docs > 0 && n_hyp > 0, "workspace_init: bad args");
+  DVD_REQUIRE(precision == DVD_PREC_FP32 || precision == DVD_PREC_BF16 || precision == DVD_PREC_BF16X3, "bad precision %d", precision);
+  Workspace w = carve(workspace, docs, n_hyp, precision);
+  if (w.total_bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", w.total_bytes, workspace_bytes); return DVD_E_WORKSPACE; }
+  if (w.sk.counters) DVD_CUDA(cudaMemsetAsync(w.sk.counters, 0, (size_t)w.sk.n_counters * sizeof(unsigned int), (cudaStream_t)stream));
+  return 0;
 }
 
 extern "C" const float* dvd_workspace_feat(void* workspace, int docs, int n_hyp, int precision) {
@@ -473,6 +508,8 @@ extern "C" int dvd_denoise_step(const dvd_weights_t* w, void* workspace, size_t 
   return denoise_step(c, x_t, init_flow, init_feat, 1, mode, table_row, ddim_a, ddim_b, pred_x0, x_prev);
 }
 
+extern "C" int dvd_debug_stop_after(int stage) { g_stop_after = stage; return 0; }
+
 extern "C" int dvd_profile_begin(void) {
   for (auto& v : g_prof.ev) { for (auto e : v) cudaEventDestroy(e); v.clear(); }
   for (int i = 0; i < PC_COUNT; ++i) { g_prof.flops[i] = 0; g_prof.launches[i] = 0; }
@@ -529,15 +566,6 @@ static int sample_group(const Ctx& c, const float* x_T, const float* init_flow0,
   return 0;
 }
 
-// second stream + fork / join events of the two-group mode (created on first use, i.e. in the caller's eager warm-up call)
-struct SplitStreams { cudaStream_t aux = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
-static thread_local SplitStreams g_split;
-static int split_mode() {       // DVD_HYP_SPLIT=1 samples the hypotheses of a single document as two concurrent chains (off by default)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DVD_HYP_SPLIT"); v = e ? atoi(e) : 0; }
-  return v;
-}
-
 extern "C" int dvd_sample(const dvd_weights_t* w, void* workspace, size_t workspace_bytes, int docs, int n_hyp, int precision,
                           const float* x_T, const float* init_flow0, const float* tables, const float* t_scaled_host,
                           const float* ddim_a_host, const float* ddim_b_host, int S, const float* init_feat0, float* map_out,
@@ -546,36 +574,6 @@ extern "C" int dvd_sample(const dvd_weights_t* w, void* workspace, size_t worksp
   DVD_TRY(make_ctx(c, w, workspace, workspace_bytes, docs, n_hyp, precision, stream));
   DVD_REQUIRE(x_T && init_flow0 && tables && t_scaled_host && ddim_a_host && ddim_b_host && map_out && S > 0, "sample: bad args");
   cudaStream_t st = c.st;
-  // Experiment (DVD_HYP_SPLIT=1, off by default): the hypotheses of a document are independent until the final mean (GD:574), so they can be
-  // sampled as TWO concurrent chains on two streams (fork / join with events, capturable into one CUDA graph) in the hope that one
-  // chain's prologues, epilogues and launch gaps overlap the other's main loops.  Results are identical (every kernel is per-sample),
-  // but measured SLOWER on B200 (3.94 vs 3.70 ms per document): the half-size kernels are latency bound and take almost as long as the
-  // full-size ones.  Not used while the kernel-class profiler is on.
-  if (can_split(docs, n_hyp) && split_mode() && !g_prof.on && !init_feat0) {
-    if (!g_split.aux) {
-      DVD_CUDA(cudaStreamCreateWithFlags(&g_split.aux, cudaStreamNonBlocking));
-      DVD_CUDA(cudaEventCreateWithFlags(&g_split.fork, cudaEventDisableTiming));
-      DVD_CUDA(cudaEventCreateWithFlags(&g_split.join, cudaEventDisableTiming));
-    }
-    const int h0 = n_hyp / 2;
-    size_t off = c.ws.step_off;
-    Ctx g[2] = {c, c};
-    g[0].n_hyp = h0; g[0].ws = carve_group(c.ws, workspace, off, h0, c.tc());
-    g[1].n_hyp = n_hyp - h0; g[1].ws = carve_group(c.ws, workspace, off, n_hyp - h0, c.tc());
-    g[1].st = g_split.aux;
-    DVD_CUDA(cudaEventRecord(g_split.fork, st));
-    DVD_CUDA(cudaStreamWaitEvent(g_split.aux, g_split.fork, 0));
-    const float* x[2] = {nullptr, nullptr}; int cur[2] = {0, 0};
-    for (int it = 0; it < S; ++it)                       // enqueue the two chains step by step so that both streams stay fed in eager mode
-      for (int k = 0; k < 2; ++k) {
-        const int hb = k ? h0 : 0;
-        DVD_TRY(sample_group(g[k], x_T + (size_t)hb * 8192, init_flow0, tables, t_scaled_host, ddim_a_host, ddim_b_host, S, nullptr,
-                             c.ws.final_flow + (size_t)hb * 8192, it, it + 1, x[k], cur[k]));
-      }
-    DVD_CUDA(cudaEventRecord(g_split.join, g_split.aux));
-    DVD_CUDA(cudaStreamWaitEvent(st, g_split.join, 0));
-    return hyp_mean_clamp(c.ws.final_flow, map_out, docs, n_hyp, st);
-  }
   const float* x = nullptr; int cur = 0;
   DVD_TRY(sample_group(c, x_T, init_flow0, tables, t_scaled_host, ddim_a_host, ddim_b_host, S, init_feat0, c.ws.final_flow, 0, S, x, cur));
   return hyp_mean_clamp(c.ws.final_flow, map_out, docs, n_hyp, st);

@@ -11,7 +11,8 @@
 
 namespace dvd {
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 };
+// ACT_GELU: tanh-GELU; the tensor path evaluates it with the hardware tanh.approx (2^-11) unless ACT_GELU_EXACT (tanhf) is asked for
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_GELU_EXACT = 4 };
 
 struct Epilogue {
   const float* bias = nullptr;        // [N]
@@ -28,8 +29,12 @@ struct Epilogue {
   int ldc = 0;
   int group_rows = 0;                 // 0: identity ; else out row = row % group_rows,
   int group_col_stride = 0;           //               out col += (row / group_rows) * group_col_stride
-  __nv_bfloat16* out_bf16 = nullptr;  // optional bf16 copy of the output (same mapping, ld = ldc_bf16)
+  __nv_bfloat16* out_bf16 = nullptr;  // optional 16-bit copy of the output (same mapping, ld = ldc_bf16): bf16, or fp16 if out_f16
   int ldc_bf16 = 0;
+  // tensor path, split-precision mode (DVD_PREC_BF16X3): the operand of the NEXT GEMM is stored as a bf16 pair hi + lo with
+  // hi = bf16(v), lo = bf16(v - hi) (same mapping and ld as out_bf16); operands of the fp16 attention kernel are stored as fp16.
+  __nv_bfloat16* out_lo = nullptr;
+  int out_f16 = 0;                    // out_bf16 (and vt_out) hold IEEE fp16 instead of bf16
   // tensor path only: columns >= vt_col0 (the V projection) are ALSO written transposed for the attention kernel:
   //   vt_out[(row / 1024) * (N - vt_col0) + (col - vt_col0)][row % 1024]      i.e. V^T [sample, C_v, T = 1024]
   __nv_bfloat16* vt_out = nullptr;
@@ -40,7 +45,7 @@ __device__ __forceinline__ float apply_epilogue(const Epilogue& e, float v, int 
   if (e.bias) v += __ldg(e.bias + col);
   if (e.scale) v = v * __ldg(e.scale + col) + __ldg(e.shift + col);
   if (e.act == ACT_RELU) v = fmaxf(v, 0.f);
-  else if (e.act == ACT_GELU) v = gelu_tanh(v);
+  else if (e.act == ACT_GELU || e.act == ACT_GELU_EXACT) v = gelu_tanh(v);
   else if (e.act == ACT_SIGMOID) v = sigmoidf_(v);
   if (e.pos) v += __ldg(e.pos + (size_t)(row % e.pos_rows) * N + col);
   if (e.gate) v *= __ldg(e.gate + col);

@@ -1,15 +1,16 @@
-// tcgen05 GEMM: C[M,N] = epilogue(A[M,K] * W[N,K]^T), bf16 operands (both K-major, exactly the torch Linear layouts),
-// fp32 accumulation in tensor memory.
+// tcgen05 GEMM: C[M,N] = epilogue(A[M,K] * W[N,K]^T), 16-bit operands (both K-major, exactly the torch Linear layouts),
+// fp32 accumulation in tensor memory.  This file: tensor maps, the dispatcher and the GENERIC single-CTA kernel (any
+// M % 128 == 0, ragged N); the denoiser's shapes run on the persistent CTA-pair kernel of gemm_pair.cu.
 //
-//   * one CTA computes a 128 x BN output tile (UMMA M=128, N=BN, K=16; BN in {128, 256}); 4 warps:
+//   * one CTA computes a 128 x BN output tile (UMMA M=128, N=BN, K=16; BN in {64, 128, 256}); 8 warps:
 //       warp 0 / one lane : TMA producer  — cp.async.bulk.tensor 2-D boxes (128 x 64 bf16, SWIZZLE_128B) into a ring of stages
-//       warp 1 / one lane : MMA issuer    — 4 x tcgen05.mma per stage, tcgen05.commit frees the stage / signals the epilogue
-//       warps 0..3        : epilogue      — tcgen05.ld (32 lanes x 32 columns per warp), fused Epilogue, vector stores
-//   * smem ring sized so that two CTAs share an SM (2 x <=112 KB, 2 x <=256 TMEM columns): the epilogue of one CTA overlaps the
-//     main loop of the other, which replaces a persistent scheduler for these small (M = 2048..8192) problems.
-//   * K tails (K = 1032 for the r-embedder) are zero-filled by TMA; M/N tails are masked in the epilogue.
+//       warp 1 / one lane : MMA issuer    — 4 (bf16) or 12 (split pair: hi*hi, lo*hi, hi*lo) tcgen05.mma per stage,
+//                                           tcgen05.commit frees the stage / signals the epilogue
+//       all 8 warps       : epilogue      — tcgen05.ld (32 lanes x 32 columns per warp), fused Epilogue, vector stores
+//   * K tails (K = 1032 for the r-embedder) are zero-filled by TMA; N tails are masked in the epilogue.
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 #include <stdlib.h>
 #include <algorithm>
 
@@ -88,24 +89,6 @@ int make_tmap_image3d(CUtensorMap* out, const void* base, int elem_bytes, uint64
   return 0;
 }
 
-// ---------------------------------------------------------------------------------------- cluster helpers (TMA multicast variant)
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// one TMA box fetched from L2 ONCE and written to the same shared-memory offset of every CTA in `mask` (each destination's mbarrier
-// at the same offset receives the transaction bytes)
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-               : "memory");
-}
-// arrive (once all previously issued MMAs of this CTA have completed) on the barrier at the same offset in every CTA of `mask`
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
-
 // ---------------------------------------------------------------------------------------- optional phase trace (-DDVD_GEMM_TRACE)
 #ifdef DVD_GEMM_TRACE
 __device__ unsigned long long g_gemm_trace[2048][8];
@@ -115,38 +98,48 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #define DVD_TRACE(slot) do { } while (0)
 #endif
 
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // ---------------------------------------------------------------------------------------- kernel
 constexpr int TBM = 128, TBK = 64;
 constexpr int TC_THREADS = 256;          // warp 0: TMA producer, warp 1: MMA issuer, all 8 warps: epilogue
 
-template <int BN>
+template <int BN, bool X3>
 struct TcCfg {
-  static constexpr int STAGES = (BN == 64) ? 4 : ((BN <= 128) ? 3 : 2);   // <= 96 KB of ring -> two CTAs per SM
+  static constexpr int NOP = X3 ? 2 : 1;                                   // hi (+ lo) copies of every operand tile
+  static constexpr int STAGES = X3 ? (BN == 64 ? 3 : 2) : ((BN == 64) ? 4 : ((BN <= 128) ? 3 : 2));
   static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // power of two >= BN
-  static constexpr int A_BYTES = TBM * TBK * 2, B_BYTES = BN * TBK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int A_BYTES = TBM * TBK * 2, B_BYTES = BN * TBK * 2;    // one copy
+  static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);            // [A_hi | A_lo | B_hi | B_lo]
+  static constexpr int B_OFF = NOP * A_BYTES;
   static constexpr int CW = BN < 128 ? BN : 128;                          // columns per epilogue pass
   static constexpr int STAGE_LD = CW + 4;                                 // fp32 staging row stride (16-byte aligned, conflict-free)
   static constexpr int STAGING_BYTES = 4 * 32 * STAGE_LD * 4;             // 4 row groups x 32 rows
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static_assert(STAGING_BYTES <= RING_BYTES, "epilogue staging must fit in the (drained) operand ring");
   static constexpr int SMEM = RING_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
+  static constexpr int MIN_CTAS = SMEM <= 112 * 1024 ? 2 : 1;
+  static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 struct ConvGeom { int H, W, Cin; };      // CONV: A is an NHWC activation, K = 9 * Cin ordered [ky][kx][Cin]
 
-// CLN x CLM > 1: the CTAs of a (CLN, CLM, 1) cluster share operand tiles through TMA multicast.  The CLN CTAs of a cluster row work on
-// the same 128 rows of A, the CLM CTAs of a cluster column on the same BN rows of W: every CTA fetches 1/CLN of the A tile and 1/CLM of
-// the W tile and multicasts them, so the L2 -> SM traffic of the main loop (what bounds the 128x128 kernel: ~64 FLOP per loaded byte)
-// drops by CLN resp. CLM.  A stage may be refilled once every CTA that receives data from this one has consumed it, so the MMA
-// issuer's commit arrives on the `empty` barrier of all CTAs of its cluster row and column (CLN + CLM - 1 arrivals per phase).
-template <int BN, bool CONV, int CLN = 1, int CLM = 1>
-__global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                 int M, int N, int K, Epilogue e, ConvGeom cg) {
-  using Cfg = TcCfg<BN>;
+template <int BN, bool CONV, bool X3>
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, X3>::MIN_CTAS)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmBl, int M, int N, int K, Epilogue e, ConvGeom cg) {
+  using Cfg = TcCfg<BN, X3>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int CL = CLN * CLM;
-  static_assert(!CONV || CL == 1, "the implicit-GEMM conv path is not clustered");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES);
@@ -164,7 +157,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant
   if (threadIdx.x == 0) {
     DVD_TRACE(0);                                       // CTA start
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CLN + CLM - 1); }
+    if (X3) { prefetch_tmap(&tmAl); prefetch_tmap(&tmBl); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -172,17 +166,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   fence_before_sync();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();                       // peers' barriers are initialised before anything is multicast to them
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  // position in the cluster: rank = x + y * CLN (grid dims are multiples of the cluster dims, checked on the host)
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
-  const int cxp = crank % CLN, cyp = crank / CLN;
-  uint16_t mask_row = 0, mask_col = 0;                  // CTAs sharing my A tile / my W tile
-#pragma unroll
-  for (int i = 0; i < CLN; ++i) mask_row |= (uint16_t)(1u << (cyp * CLN + i));
-#pragma unroll
-  for (int i = 0; i < CLM; ++i) mask_col |= (uint16_t)(1u << (i * CLN + cxp));
   pdl_wait();                                           // everything above overlapped the previous kernel's tail
   if (threadIdx.x == 0) DVD_TRACE(1);                   // prologue done, predecessor finished
 
@@ -200,23 +185,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant
         mbar_wait(&empty[s], (it & 1) ^ 1);
         uint8_t* a = smem + s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        if (CL > 1) {
-          // my slice of the A tile (rows cxp * 128/CLN ...) to the cluster row, my slice of the W tile to the cluster column;
-          // the tensor-map boxes are 128/CLN and min(128, BN/CLM) rows tall
-          constexpr int AR = TBM / CLN, BR = BN / CLM, BBOX = BR > 128 ? 128 : BR;
-          tma_load_2d_mc(a + cxp * AR * TBK * 2, &tmA, &full[s], kb * TBK, m0 + cxp * AR, mask_row);
 #pragma unroll
-          for (int j = 0; j < BR / BBOX; ++j)
-            tma_load_2d_mc(a + Cfg::A_BYTES + (cyp * BR + j * BBOX) * TBK * 2, &tmB, &full[s], kb * TBK, n0 + cyp * BR + j * BBOX, mask_col);
-        } else {
+        for (int o = 0; o < Cfg::NOP; ++o) {
+          const CUtensorMap* ta = o ? &tmAl : &tmA;
+          const CUtensorMap* tb = o ? &tmBl : &tmB;
+          uint8_t* ad = a + o * Cfg::A_BYTES;
+          uint8_t* bd = a + Cfg::B_OFF + o * Cfg::B_BYTES;
           if (CONV) {
             const int tap = kb / cblocks, cb = kb % cblocks;
-            tma_load_4d(a, &tmA, &full[s], cb * 64, cx + tap % 3 - 1, cy + tap / 3 - 1, cn);
+            tma_load_4d(ad, ta, &full[s], cb * 64, cx + tap % 3 - 1, cy + tap / 3 - 1, cn);
           } else {
-            tma_load_2d(a, &tmA, &full[s], kb * TBK, m0);
+            tma_load_2d(ad, ta, &full[s], kb * TBK, m0);
           }
-          tma_load_2d(a + Cfg::A_BYTES, &tmB, &full[s], kb * TBK, n0);
-          if (BN == 256) tma_load_2d(a + Cfg::A_BYTES + 128 * TBK * 2, &tmB, &full[s], kb * TBK, n0 + 128);
+          tma_load_2d(bd, tb, &full[s], kb * TBK, n0);
+          if (BN == 256) tma_load_2d(bd + 128 * TBK * 2, tb, &full[s], kb * TBK, n0 + 128);
         }
       }
     }
@@ -231,14 +213,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant
         if (kb == 0) DVD_TRACE(2);                      // first stage landed
         if (kb == nkb - 1) DVD_TRACE(3);                // last stage landed
         fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES), b_addr = a_addr + Cfg::A_BYTES;
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES), b_addr = a_addr + Cfg::B_OFF;
 #pragma unroll
         for (int k = 0; k < TBK / 16; ++k) {
           // advancing K inside the 128-byte swizzle atom = +32 bytes on the start address
-          mma_f16_ss(tmem_base, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+          const uint64_t ah = make_desc_k_sw128(a_addr + k * 32), bh = make_desc_k_sw128(b_addr + k * 32);
+          mma_f16_ss(tmem_base, ah, bh, idesc, (kb | k) ? 1u : 0u);
+          if (X3) {
+            mma_f16_ss(tmem_base, make_desc_k_sw128(a_addr + Cfg::A_BYTES + k * 32), bh, idesc, 1u);       // lo * hi
+            mma_f16_ss(tmem_base, ah, make_desc_k_sw128(b_addr + Cfg::B_BYTES + k * 32), idesc, 1u);       // hi * lo
+          }
         }
-        if (CL > 1) mma_commit_mc(&empty[s], mask_row | mask_col);   // every CTA that sends me operands learns the stage is free
-        else        mma_commit(&empty[s]);               // stage reusable once these MMAs have read it
+        mma_commit(&empty[s]);                           // stage reusable once these MMAs have read it
       }
       mma_commit(tmem_full);                             // accumulator complete
     }
@@ -246,9 +232,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant
   }
 
   // ===== epilogue.  tmem_full => every MMA has retired, so every TMA write has been consumed: the operand ring is dead
-  // and is reused as an fp32 staging tile.  The epilogue is a third of a batch-1 launch (tools/gemm_trace.py), so all 8 warps take
-  // part: warps w and w+4 own the same 32 rows (a warp can only read the TMEM lanes 32*(w%4)..+31) and split the columns in
-  // phase 1 and the rows in phase 2, synchronised by a 64-thread named barrier per row group.
+  // and is reused as an fp32 staging tile.  All 8 warps take part: warps w and w+4 own the same 32 rows (a warp can only read the
+  // TMEM lanes 32*(w%4)..+31) and split the columns in phase 1 and the rows in phase 2, synchronised by a 64-thread named
+  // barrier per row group.
   //   Phase 1 (thread = row, TMEM lane): TMEM -> registers -> staging (+ the transposed V^T store, which is naturally
   //   coalesced in this mapping).  Phase 2 (lane = 4 consecutive columns): staging -> fused epilogue -> fully coalesced
   //   512-byte row segments in global memory.
@@ -281,21 +267,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant
           const float4 b4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
           bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
         }
-        __nv_bfloat16* o = e.vt_out + ((size_t)(row_t >> 10) * (N - e.vt_col0) + (col0 - e.vt_col0)) * 1024 + (row_t & 1023);
+        uint16_t* o = reinterpret_cast<uint16_t*>(e.vt_out) + ((size_t)(row_t >> 10) * (N - e.vt_col0) + (col0 - e.vt_col0)) * 1024 + (row_t & 1023);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[(size_t)j * 1024] = __float2bfloat16_rn(__uint_as_float(r[j]) + bv[j]);
+        for (int j = 0; j < 32; ++j) o[(size_t)j * 1024] = cvt16(__uint_as_float(r[j]) + bv[j], e.out_f16);
       }
     }
     pair_sync();                                         // both column halves of the row group are staged
     // ---- phase 2: this warp finishes rows wh*16 .. wh*16+15 of the group
     const int col = n0 + pass * CW + 4 * lane;
     if (4 * lane < CW && col < N) {
-      float4 cb = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f), ct = cb, cgate = cs;
-      if (e.bias) cb = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-      if (e.scale) { cs = __ldg(reinterpret_cast<const float4*>(e.scale + col)); ct = __ldg(reinterpret_cast<const float4*>(e.shift + col)); }
-      if (e.gate) cgate = __ldg(reinterpret_cast<const float4*>(e.gate + col));
-      const bool has_scale = e.scale != nullptr, has_gate = e.gate != nullptr;
-      const int act = e.act;
+      const EpiCols ec = load_epi_cols(e, col);
 #pragma unroll 1
       for (int r0 = wh * 16; r0 < wh * 16 + 16; r0 += 8) {
         float4 a[8], q[8], p[8];
@@ -320,22 +301,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = m0 + wq * 32 + r0 + i;
-          float v[4] = {a[i].x + cb.x, a[i].y + cb.y, a[i].z + cb.z, a[i].w + cb.w};
-          if (has_scale) { v[0] = v[0] * cs.x + ct.x; v[1] = v[1] * cs.y + ct.y; v[2] = v[2] * cs.z + ct.z; v[3] = v[3] * cs.w + ct.w; }
-          if (act == ACT_RELU) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-          else if (act == ACT_GELU) { v[0] = gelu_tanh_fast(v[0]); v[1] = gelu_tanh_fast(v[1]); v[2] = gelu_tanh_fast(v[2]); v[3] = gelu_tanh_fast(v[3]); }
-          else if (act == ACT_SIGMOID) { v[0] = sigmoidf_(v[0]); v[1] = sigmoidf_(v[1]); v[2] = sigmoidf_(v[2]); v[3] = sigmoidf_(v[3]); }
-          if (e.pos) { v[0] += p[i].x; v[1] += p[i].y; v[2] += p[i].z; v[3] += p[i].w; }
-          if (has_gate) { v[0] *= cgate.x; v[1] *= cgate.y; v[2] *= cgate.z; v[3] *= cgate.w; }
-          if (e.resid) { v[0] += q[i].x; v[1] += q[i].y; v[2] += q[i].z; v[3] += q[i].w; }
+          float v[4];
+          apply_epi4(ec, a[i], e.pos != nullptr, p[i], e.resid != nullptr, q[i], v);
           int orow, ocol;
           epilogue_dest(e, row, col, orow, ocol);
-          if (e.out) *reinterpret_cast<float4*>(e.out + (size_t)orow * e.ldc + ocol) = make_float4(v[0], v[1], v[2], v[3]);
-          if (e.out_bf16) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-            uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(e.out_bf16 + (size_t)orow * e.ldc_bf16 + ocol) = u;
-          }
+          store_tc_out4(e, orow, ocol, v);
         }
       }
     }
@@ -345,33 +315,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tc(const __grid_constant
   __syncthreads();
   if (threadIdx.x == 0) DVD_TRACE(5);                   // epilogue done
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  if (CL > 1) cluster_sync_all();                       // peers may still be arriving on my `empty` barriers
 }
 
-template <int BN, int CLN, int CLM>
-static int launch_tc_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epilogue& e, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DVD_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, false, CLN, CLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
-    attr_set = true;
-  }
-  dim3 grid(cdiv(N, BN), cdiv(M, TBM));
-  ConvGeom cg{0, 0, 0};
-  DVD_CUDA(launch_pdl_cluster(1, k_gemm_tc<BN, false, CLN, CLM>, grid, dim3(TC_THREADS), (size_t)TcCfg<BN>::SMEM, st, CLN, CLM, tmA, tmB, M, N, K, e, cg));
-  DVD_LAUNCH_CHECK("k_gemm_tc (cluster)");
-  return 0;
-}
-
-template <int BN, bool CONV>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epilogue& e, ConvGeom cg, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DVD_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
-    attr_set = true;
-  }
+template <int BN, bool CONV, bool X3>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmAl, const CUtensorMap& tmB, const CUtensorMap& tmBl, int M, int N, int K,
+                     const Epilogue& e, ConvGeom cg, cudaStream_t st) {
+  using Cfg = TcCfg<BN, X3>;
+  auto kern = k_gemm_tc<BN, CONV, X3>;
+  DVD_SET_MAX_SMEM(kern, Cfg::SMEM);
   const int my = cdiv(M, TBM), gy = my > 32768 ? 32768 : my;
   dim3 grid(cdiv(N, BN), gy, cdiv(my, gy));
-  DVD_CUDA(launch_pdl(1, k_gemm_tc<BN, CONV>, grid, dim3(TC_THREADS), (size_t)TcCfg<BN>::SMEM, st, tmA, tmB, M, N, K, e, cg));
+  DVD_CUDA(launch_pdl(1, k_gemm_tc<BN, CONV, X3>, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, tmA, tmAl, tmB, tmBl, M, N, K, e, cg));
   DVD_LAUNCH_CHECK("k_gemm_tc");
   return 0;
 }
@@ -380,107 +334,77 @@ static int check_epilogue(const Epilogue& e, int N) {
   DVD_REQUIRE(N % 4 == 0, "gemm_tc: N must be a multiple of 4");
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   DVD_REQUIRE(al(e.bias) && al(e.scale) && al(e.shift) && al(e.gate) && al(e.pos) && al(e.resid) && al(e.out) &&
-              (reinterpret_cast<uintptr_t>(e.out_bf16) & 7) == 0, "gemm_tc: epilogue pointers must be 16-byte aligned");
+              (reinterpret_cast<uintptr_t>(e.out_bf16) & 7) == 0 && (reinterpret_cast<uintptr_t>(e.out_lo) & 7) == 0,
+              "gemm_tc: epilogue pointers must be 16-byte aligned");
   DVD_REQUIRE(e.ldc % 4 == 0 && e.ldr % 4 == 0 && e.ldc_bf16 % 4 == 0 && e.group_col_stride % 4 == 0, "gemm_tc: epilogue leading dims %% 4");
+  DVD_REQUIRE(!e.out_lo || (e.out_bf16 && !e.out_f16), "gemm_tc: out_lo needs out_bf16 (bf16 pair)");
   DVD_REQUIRE(!e.vt_out || (e.vt_col0 % 32 == 0 && N % 32 == 0 && !e.scale && !e.act && !e.pos && !e.gate && !e.resid),
               "gemm_tc: the V^T output supports a bias-only epilogue with vt_col0 %% 32 == 0");
   return 0;
 }
 
-int gemm_tc2_dispatch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e,
-                      int conv_b, int conv_h, int conv_w, int conv_cin, cudaStream_t st);
-static bool use_v1() {
+static bool use_v1() {       // DVD_GEMM_V1=1: force the generic single-CTA kernel (A/B tests, tools/gemm_bench.py)
   static int v = -1;
   if (v < 0) { const char* s = getenv("DVD_GEMM_V1"); v = (s && s[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 
-int gemm_tc3_dispatch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e, int bn,
-                      cudaStream_t st);
-static int v3_mode() {      // DVD_GEMM_V3: 0 = off, 1 = pair kernel wherever the shape allows, 2 = heuristic
-  static int v = -1;
-  if (v < 0) { const char* s = getenv("DVD_GEMM_V3"); v = s ? atoi(s) : 0; }
-  return v;
-}
-static bool force_v2() {
-  static int v = -1;
-  if (v < 0) { const char* s = getenv("DVD_GEMM_V2"); v = (s && s[0] == '1') ? 1 : 0; }
-  return v == 1;
+template <bool CONV, bool X3>
+static int launch_tc_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmAl, const CUtensorMap& tmB, const CUtensorMap& tmBl, int M, int N,
+                        int K, const Epilogue& e, ConvGeom cg, cudaStream_t st) {
+  if (bn == 256) return launch_tc<256, CONV, X3>(tmA, tmAl, tmB, tmBl, M, N, K, e, cg, st);
+  if (bn == 64) return launch_tc<64, CONV, X3>(tmA, tmAl, tmB, tmBl, M, N, K, e, cg, st);
+  return launch_tc<128, CONV, X3>(tmA, tmAl, tmB, tmBl, M, N, K, e, cg, st);
 }
 
-int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e, cudaStream_t st) {
-  DVD_REQUIRE(A && W && (e.out || e.out_bf16), "gemm_tc: null pointer");
+int gemm_tc(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, const TcScratch* sk, cudaStream_t st) {
+  DVD_REQUIRE(A.hi && W.hi && (e.out || e.out_bf16), "gemm_tc: null pointer");
   DVD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && M % 128 == 0, "gemm_tc: bad shape M=%d N=%d K=%d (M must be a multiple of 128)", M, N, K);
+  DVD_REQUIRE((A.lo != nullptr) == (W.lo != nullptr), "gemm_tc: A and W must both be split pairs or both plain");
   int rc = check_epilogue(e, N); if (rc) return rc;
-  if (v3_mode() == 1 && M % 256 == 0 && N % 128 == 0) {
-    int bn = (N % 256 == 0) ? 256 : 128;
-    if (const char* f = getenv("DVD_GEMM_BN")) { int v = atoi(f); if ((v == 128 || v == 256) && N % v == 0) bn = v; }
-    return gemm_tc3_dispatch(A, lda, W, ldw, M, N, K, e, bn, st);
+  if (!use_v1() && gemm_pair_supported(M, N, K, false)) return gemm_pair_dispatch(A, W, M, N, K, e, 0, 0, 0, 0, sk, st);
+  const bool x3 = A.lo != nullptr;
+  // wide tiles only when they still fill the machine
+  const bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) * 100 >= 190LL * sm_count());
+  const int bn = (N <= 64) ? 64 : (wide ? 256 : 128);
+  CUtensorMap tmA, tmB, tmAl, tmBl;
+  rc = make_tmap_bf16_2d(&tmA, A.hi, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, 128, 64); if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W.hi, (uint64_t)N, (uint64_t)K, (uint64_t)W.ld, bn == 64 ? 64 : 128, 64); if (rc) return rc;
+  tmAl = tmA; tmBl = tmB;
+  if (x3) {
+    rc = make_tmap_bf16_2d(&tmAl, A.lo, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, 128, 64); if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmBl, W.lo, (uint64_t)N, (uint64_t)K, (uint64_t)W.ld, bn == 64 ? 64 : 128, 64); if (rc) return rc;
   }
-  // Measured on B200 (profiles/r1_gemm_microbench.txt): the persistent 128x256 kernel wins once there are >= 4 waves of wide
-  // tiles (1.1 PFLOP/s at M = 16384); the small M = 2048 problems of a single document are latency-bound and run faster as two
-  // co-resident 128x128 CTAs per SM.
-  if (!use_v1() && (force_v2() || (N % 256 == 0 && (long long)(M / 128) * (N / 256) >= 4 * kSMs)))
-    return gemm_tc2_dispatch(A, lda, W, ldw, M, N, K, e, 0, 0, 0, 0, st);
-  // wide tiles only when they still fill the machine (>= ~1 wave of 2 CTAs/SM)
-  bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) * 100 >= 190LL * kSMs);   // >= ~1.9 SM-fulls of 128x256 tiles (2 CTAs/SM)
-  if (const char* f = getenv("DVD_GEMM_WIDE")) wide = (N % 256 == 0) && atoi(f) == 1;     // tuning override
-  const bool narrow = (N <= 64);
-  // 128x96 and 128x192 (one CTA per SM, 5-stage ring) tiles were measured on the N = 1536 shapes: no gain over 128x128 (the main loop
-  // already runs at the tensor rate of two co-resident CTAs; the launches are bound by prologue + epilogue, see tools/gemm_trace.py).
-  CUtensorMap tmA, tmB;
-  // TMA-multicast clusters (experiment, OFF by default): DVD_GEMM_CLUSTER=22 / 12 / 21 shares the A tile along N and / or the W tile
-  // along M inside (2,2) / (1,2) / (2,1) clusters.  Measured on B200 (tools/gemm_bench.py): correct, but 5-10% SLOWER than independent
-  // CTAs on every denoiser shape (e.g. 2048x1536x1536: 25.6 vs 23.6 us; 16384x4608x1536: 292 vs 235 us) - halving the L2 reads does not
-  // help because the main loop is bound by what each SM can take in, and the cluster couples the progress of its CTAs.
-  if (!narrow) {
-    static const int cl_env = getenv("DVD_GEMM_CLUSTER") ? atoi(getenv("DVD_GEMM_CLUSTER")) : 0;
-    const int bn = wide ? 256 : 128;
-    const int gx = N / bn, gy = M / 128;
-    int cl = 0;
-    if (N % bn == 0 && cl_env != 0 && gy <= 32768) {
-      if (gx % 2 == 0 && gy % 2 == 0) cl = 22; else if (gy % 2 == 0) cl = 12; else if (gx % 2 == 0) cl = 21;
-      if (cl_env == 12 && gy % 2 == 0) cl = 12;
-      if (cl_env == 21 && gx % 2 == 0) cl = 21;
-    }
-    if (cl) {
-      const int cln = cl / 10, clm = cl % 10;
-      rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128 / cln, 64); if (rc) return rc;
-      rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, std::min(128, bn / clm), 64); if (rc) return rc;
-      if (wide) {
-        if (cl == 22) return launch_tc_cluster<256, 2, 2>(tmA, tmB, M, N, K, e, st);
-        if (cl == 12) return launch_tc_cluster<256, 1, 2>(tmA, tmB, M, N, K, e, st);
-        return launch_tc_cluster<256, 2, 1>(tmA, tmB, M, N, K, e, st);
-      }
-      if (cl == 22) return launch_tc_cluster<128, 2, 2>(tmA, tmB, M, N, K, e, st);
-      if (cl == 12) return launch_tc_cluster<128, 1, 2>(tmA, tmB, M, N, K, e, st);
-      return launch_tc_cluster<128, 2, 1>(tmA, tmB, M, N, K, e, st);
-    }
-  }
-  rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64); if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, narrow ? 64 : 128, 64); if (rc) return rc;
   ConvGeom cg{0, 0, 0};
-  if (wide) return launch_tc<256, false>(tmA, tmB, M, N, K, e, cg, st);
-  if (narrow) return launch_tc<64, false>(tmA, tmB, M, N, K, e, cg, st);
-  return launch_tc<128, false>(tmA, tmB, M, N, K, e, cg, st);
+  return x3 ? launch_tc_bn<false, true>(bn, tmA, tmAl, tmB, tmBl, M, N, K, e, cg, st)
+            : launch_tc_bn<false, false>(bn, tmA, tmAl, tmB, tmBl, M, N, K, e, cg, st);
 }
 
-// 3x3 / pad 1 / stride 1 convolution as an implicit GEMM: in NHWC bf16 [B,H,W,Cin], Wt [Cout, 9*Cin] ([ky][kx][Cin]),
-// out NHWC [B,H,W,Cout] through the Epilogue (bias + ReLU, bf16 and/or fp32).
-int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* Wt, int B, int H, int Wd, int Cin, int Cout, const Epilogue& e,
-                    cudaStream_t st) {
-  DVD_REQUIRE(in && Wt && (e.out || e.out_bf16), "conv3x3_tc: null pointer");
+// 3x3 / pad 1 / stride 1 convolution as an implicit GEMM: in NHWC [B,H,W,Cin], Wt [Cout, 9*Cin] ([ky][kx][Cin]),
+// out NHWC [B,H,W,Cout] through the Epilogue (bias + ReLU, 16-bit and/or fp32).
+int conv3x3_tc(const TcMat& in, const TcMat& Wt, int B, int H, int Wd, int Cin, int Cout, const Epilogue& e, cudaStream_t st) {
+  DVD_REQUIRE(in.hi && Wt.hi && (e.out || e.out_bf16), "conv3x3_tc: null pointer");
   DVD_REQUIRE(Cin % 64 == 0 && Wd % 128 == 0 && (Cout == 64 || Cout % 128 == 0), "conv3x3_tc: unsupported shape Cin=%d W=%d Cout=%d", Cin, Wd, Cout);
+  DVD_REQUIRE((in.lo != nullptr) == (Wt.lo != nullptr), "conv3x3_tc: activation and weight must both be split pairs or both plain");
   const int M = B * H * Wd, K = 9 * Cin;
   int rc = check_epilogue(e, Cout); if (rc) return rc;
-  if (!use_v1() && force_v2()) return gemm_tc2_dispatch(in, 0, Wt, K, M, Cout, K, e, B, H, Wd, Cin, st);
-  CUtensorMap tmA, tmB;
-  rc = make_tmap_bf16_nhwc(&tmA, in, (uint64_t)B, (uint64_t)H, (uint64_t)Wd, (uint64_t)Cin); if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)Cout, (uint64_t)K, (uint64_t)K, Cout == 64 ? 64 : 128, 64); if (rc) return rc;
+  if (!use_v1() && gemm_pair_supported(M, Cout, K, true)) {
+    TcMat w = Wt; w.ld = K;
+    return gemm_pair_dispatch(in, w, M, Cout, K, e, B, H, Wd, Cin, nullptr, st);
+  }
+  const bool x3 = in.lo != nullptr;
+  const int bn = Cout == 64 ? 64 : ((Cout % 256 == 0 && (long long)(M / 128) * (Cout / 256) >= 2LL * sm_count()) ? 256 : 128);
+  CUtensorMap tmA, tmB, tmAl, tmBl;
+  rc = make_tmap_bf16_nhwc(&tmA, in.hi, (uint64_t)B, (uint64_t)H, (uint64_t)Wd, (uint64_t)Cin); if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, Wt.hi, (uint64_t)Cout, (uint64_t)K, (uint64_t)K, bn == 64 ? 64 : 128, 64); if (rc) return rc;
+  tmAl = tmA; tmBl = tmB;
+  if (x3) {
+    rc = make_tmap_bf16_nhwc(&tmAl, in.lo, (uint64_t)B, (uint64_t)H, (uint64_t)Wd, (uint64_t)Cin); if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmBl, Wt.lo, (uint64_t)Cout, (uint64_t)K, (uint64_t)K, bn == 64 ? 64 : 128, 64); if (rc) return rc;
+  }
   ConvGeom cg{H, Wd, Cin};
-  if (Cout == 64) return launch_tc<64, true>(tmA, tmB, M, Cout, K, e, cg, st);
-  if (Cout % 256 == 0 && (long long)(M / 128) * (Cout / 256) >= 2 * kSMs) return launch_tc<256, true>(tmA, tmB, M, Cout, K, e, cg, st);
-  return launch_tc<128, true>(tmA, tmB, M, Cout, K, e, cg, st);
+  return x3 ? launch_tc_bn<true, true>(bn, tmA, tmAl, tmB, tmBl, M, Cout, K, e, cg, st)
+            : launch_tc_bn<true, false>(bn, tmA, tmAl, tmB, tmBl, M, Cout, K, e, cg, st);
 }
 
 }  // namespace dvd

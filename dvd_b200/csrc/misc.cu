@@ -1,4 +1,5 @@
 #include "misc.cuh"
+#include "tc_epilogue.cuh"
 #include <algorithm>
 
 namespace dvd {
@@ -6,8 +7,8 @@ namespace dvd {
 // ------------------------------------------------------------------------------------------ layer norm
 template <int NV>   // float4 per lane: C = 128 * NV
 __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ in, int ldin, float* __restrict__ out, int ldo,
-                                                   __nv_bfloat16* __restrict__ out16, int ldo16, int rows, float eps,
-                                                   const float* __restrict__ w, const float* __restrict__ b,
+                                                   __nv_bfloat16* __restrict__ out16, __nv_bfloat16* __restrict__ out16_lo, int ldo16,
+                                                   int rows, float eps, const float* __restrict__ w, const float* __restrict__ b,
                                                    const float* __restrict__ msh, const float* __restrict__ msc) {
   pdl_trigger();
   pdl_wait();
@@ -42,21 +43,23 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ in,
     }
     if (out) *reinterpret_cast<float4*>(out + (size_t)row * ldo + c0) = make_float4(y[0], y[1], y[2], y[3]);
     if (out16) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
-      uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      uint2 u, l;
+      split_bf16x2(y[0], y[1], u.x, l.x);
+      split_bf16x2(y[2], y[3], u.y, l.y);
       *reinterpret_cast<uint2*>(out16 + (size_t)row * ldo16 + c0) = u;
+      if (out16_lo) *reinterpret_cast<uint2*>(out16_lo + (size_t)row * ldo16 + c0) = l;
     }
   }
 }
 
-int layernorm(const float* in, int ldin, float* out, int ldo, __nv_bfloat16* out16, int ldo16, int rows, int C, float eps,
-              const float* w, const float* b, const float* msh, const float* msc, cudaStream_t st) {
+int layernorm(const float* in, int ldin, float* out, int ldo, __nv_bfloat16* out16, __nv_bfloat16* out16_lo, int ldo16, int rows, int C,
+              float eps, const float* w, const float* b, const float* msh, const float* msc, cudaStream_t st) {
   DVD_REQUIRE(in && (out || out16) && rows > 0, "layernorm: bad args");
   DVD_REQUIRE(C == 384 || C == 1536, "layernorm: C must be 384 or 1536 (got %d)", C);
   DVD_REQUIRE(ldin % 4 == 0 && ldo % 4 == 0 && ldo16 % 4 == 0, "layernorm: ld %% 4");
   dim3 grid(cdiv(rows, 8));
-  if (C == 384) DVD_CUDA(launch_pdl(4, k_layernorm<3>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, ldo16, rows, eps, w, b, msh, msc));
-  else          DVD_CUDA(launch_pdl(4, k_layernorm<12>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, ldo16, rows, eps, w, b, msh, msc));
+  if (C == 384) DVD_CUDA(launch_pdl(4, k_layernorm<3>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, out16_lo, ldo16, rows, eps, w, b, msh, msc));
+  else          DVD_CUDA(launch_pdl(4, k_layernorm<12>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, out16_lo, ldo16, rows, eps, w, b, msh, msc));
   DVD_LAUNCH_CHECK("k_layernorm");
   return 0;
 }
@@ -101,7 +104,8 @@ int maxpool2_nhwc(const float* in, float* out, int B, int H, int W, int C, cudaS
 
 // one thread = one (pixel, tap pair): 8 of the 16-byte chunks of a 128-byte output row; chunks 5..7 (k >= 40) are zero and
 // chunk 4 holds tap 8 + zeros
-__global__ void __launch_bounds__(256) k_im2col_c4(const float4* __restrict__ in, uint4* __restrict__ out, int H, int W, size_t total) {
+__global__ void __launch_bounds__(256) k_im2col_c4(const float4* __restrict__ in, uint4* __restrict__ out, uint4* __restrict__ out_lo, int H, int W,
+                                                   size_t total) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // total = B*H*W*8 chunks
   if (i >= total) return;
   const int chunk = i & 7; const size_t pix = i >> 3;
@@ -116,23 +120,24 @@ __global__ void __launch_bounds__(256) k_im2col_c4(const float4* __restrict__ in
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) v[t] = __ldg(in + (b * H + yy) * W + xx);
     }
   }
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0].x, v[0].y), p1 = __floats2bfloat162_rn(v[0].z, v[0].w);
-  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[1].x, v[1].y), p3 = __floats2bfloat162_rn(v[1].z, v[1].w);
-  uint4 o;
-  o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-  o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+  uint4 o, l;
+  split_bf16x2(v[0].x, v[0].y, o.x, l.x); split_bf16x2(v[0].z, v[0].w, o.y, l.y);
+  split_bf16x2(v[1].x, v[1].y, o.z, l.z); split_bf16x2(v[1].z, v[1].w, o.w, l.w);
   out[i] = o;
+  if (out_lo) out_lo[i] = l;
 }
-int im2col3x3_c4_bf16(const float* in, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st) {
+int im2col3x3_c4_bf16(const float* in, __nv_bfloat16* out, __nv_bfloat16* out_lo, int B, int H, int W, cudaStream_t st) {
   DVD_REQUIRE(in && out && B > 0, "im2col: bad args");
   size_t total = (size_t)B * H * W * 8;
-  k_im2col_c4<<<cdiv(total, 256), 256, 0, st>>>((const float4*)in, (uint4*)out, H, W, total);
+  k_im2col_c4<<<cdiv(total, 256), 256, 0, st>>>((const float4*)in, (uint4*)out, (uint4*)out_lo, H, W, total);
   DVD_LAUNCH_CHECK("k_im2col_c4");
   return 0;
 }
 
-// 2x2 max pool on bf16 NHWC (8 channels = 16 bytes per thread); writes bf16 and/or fp32
-__global__ void k_maxpool2_bf16(const uint4* __restrict__ in, uint4* __restrict__ out16, float* __restrict__ out32, int B, int H, int W, int C8) {
+// 2x2 max pool on bf16 NHWC (8 channels = 16 bytes per thread); the input may be a split pair (value = hi + lo), the output is
+// written as bf16 (hi + optional lo) and / or fp32
+__global__ void k_maxpool2_bf16(const uint4* __restrict__ in, const uint4* __restrict__ in_lo, uint4* __restrict__ out16,
+                                uint4* __restrict__ out16_lo, float* __restrict__ out32, int B, int H, int W, int C8) {
   const int Ho = H / 2, Wo = W / 2;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)B * Ho * Wo * C8;
@@ -140,31 +145,42 @@ __global__ void k_maxpool2_bf16(const uint4* __restrict__ in, uint4* __restrict_
   int c = i % C8; size_t r = i / C8;
   int xo = r % Wo; r /= Wo;
   int yo = r % Ho; int b = r / Ho;
-  const uint4* p = in + (((size_t)b * H + 2 * yo) * W + 2 * xo) * C8 + c;
-  uint4 q[4] = {__ldg(p), __ldg(p + C8), __ldg(p + (size_t)W * C8), __ldg(p + (size_t)W * C8 + C8)};
-  uint4 m;
-  uint32_t* mw = reinterpret_cast<uint32_t*>(&m);
+  const size_t base = (((size_t)b * H + 2 * yo) * W + 2 * xo) * C8 + c;
+  const size_t offs[4] = {0, (size_t)C8, (size_t)W * C8, (size_t)W * C8 + C8};
+  float m[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&reinterpret_cast<uint32_t*>(&q[0])[k]);
+  for (int t = 0; t < 4; ++t) {
+    const uint4 q = __ldg(in + base + offs[t]);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+    float f[8] = {__low2float(h[0]), __high2float(h[0]), __low2float(h[1]), __high2float(h[1]),
+                  __low2float(h[2]), __high2float(h[2]), __low2float(h[3]), __high2float(h[3])};
+    if (in_lo) {
+      const uint4 ql = __ldg(in_lo + base + offs[t]);
+      const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&ql);
 #pragma unroll
-    for (int t = 1; t < 4; ++t) a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&reinterpret_cast<uint32_t*>(&q[t])[k]));
-    mw[k] = *reinterpret_cast<uint32_t*>(&a);
-  }
-  if (out16) out16[i] = m;
-  if (out32) {
-    float* o = out32 + i * 8;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&mw[k]);
-      o[2 * k] = __low2float(a); o[2 * k + 1] = __high2float(a);
+      for (int k = 0; k < 4; ++k) { f[2 * k] += __low2float(hl[k]); f[2 * k + 1] += __high2float(hl[k]); }
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = t == 0 ? f[k] : fmaxf(m[k], f[k]);
+  }
+  if (out16) {
+    uint4 o, l;
+    split_bf16x2(m[0], m[1], o.x, l.x); split_bf16x2(m[2], m[3], o.y, l.y);
+    split_bf16x2(m[4], m[5], o.z, l.z); split_bf16x2(m[6], m[7], o.w, l.w);
+    out16[i] = o;
+    if (out16_lo) out16_lo[i] = l;
+  }
+  if (out32) {
+    float4* o = reinterpret_cast<float4*>(out32 + i * 8);
+    o[0] = make_float4(m[0], m[1], m[2], m[3]);
+    o[1] = make_float4(m[4], m[5], m[6], m[7]);
   }
 }
-int maxpool2_nhwc_bf16(const __nv_bfloat16* in, __nv_bfloat16* out16, float* out32, int B, int H, int W, int C, cudaStream_t st) {
+int maxpool2_nhwc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* in_lo, __nv_bfloat16* out16, __nv_bfloat16* out16_lo, float* out32, int B,
+                       int H, int W, int C, cudaStream_t st) {
   DVD_REQUIRE(in && (out16 || out32) && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bf16: bad args");
   size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-  k_maxpool2_bf16<<<cdiv(total, 256), 256, 0, st>>>((const uint4*)in, (uint4*)out16, out32, B, H, W, C / 8);
+  k_maxpool2_bf16<<<cdiv(total, 256), 256, 0, st>>>((const uint4*)in, (const uint4*)in_lo, (uint4*)out16, (uint4*)out16_lo, out32, B, H, W, C / 8);
   DVD_LAUNCH_CHECK("k_maxpool2_bf16");
   return 0;
 }
@@ -190,18 +206,20 @@ int nhwc_to_nchw(const float* in, float* out, int B, int H, int W, int C, cudaSt
 }
 
 // ------------------------------------------------------------------------------------------ patchify
-__device__ __forceinline__ void store4(float* A, __nv_bfloat16* A16, size_t off, float a, float b, float c, float d) {
+struct Out16 { __nv_bfloat16* hi; __nv_bfloat16* lo; };      // bf16 destination: plain (lo == null) or split pair
+__device__ __forceinline__ void store4(float* A, Out16 A16, size_t off, float a, float b, float c, float d) {
   if (A) *reinterpret_cast<float4*>(A + off) = make_float4(a, b, c, d);
-  if (A16) {
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
-    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-    *reinterpret_cast<uint2*>(A16 + off) = u;
+  if (A16.hi) {
+    uint2 u, l;
+    split_bf16x2(a, b, u.x, l.x);
+    split_bf16x2(c, d, u.y, l.y);
+    *reinterpret_cast<uint2*>(A16.hi + off) = u;
+    if (A16.lo) *reinterpret_cast<uint2*>(A16.lo + off) = l;
   }
 }
 
 // block = one (b, h) token row x 32 channels; smem tile gives coalesced reads AND writes
-__global__ void __launch_bounds__(256) k_patchify_nchw(const float* __restrict__ in, float* __restrict__ A,
-                                                       __nv_bfloat16* __restrict__ A16, int lda, int C) {
+__global__ void __launch_bounds__(256) k_patchify_nchw(const float* __restrict__ in, float* __restrict__ A, Out16 A16, int lda, int C) {
   __shared__ float tile[32][2][65];
   const int h = blockIdx.x, c0 = blockIdx.y * 32, b = blockIdx.z;
   for (int i = threadIdx.x; i < 32 * 128; i += 256) {
@@ -217,15 +235,14 @@ __global__ void __launch_bounds__(256) k_patchify_nchw(const float* __restrict__
     store4(A, A16, off, tile[cc][0][2 * w], tile[cc][0][2 * w + 1], tile[cc][1][2 * w], tile[cc][1][2 * w + 1]);
   }
 }
-int patchify_nchw(const float* in, float* A, __nv_bfloat16* A16, int lda, int B, int C, cudaStream_t st) {
+int patchify_nchw(const float* in, float* A, __nv_bfloat16* A16, __nv_bfloat16* A16_lo, int lda, int B, int C, cudaStream_t st) {
   DVD_REQUIRE(in && (A || A16) && lda % 4 == 0 && lda >= 4 * C, "patchify_nchw: bad args");
-  k_patchify_nchw<<<dim3(32, cdiv(C, 32), B), 256, 0, st>>>(in, A, A16, lda, C);
+  k_patchify_nchw<<<dim3(32, cdiv(C, 32), B), 256, 0, st>>>(in, A, Out16{A16, A16_lo}, lda, C);
   DVD_LAUNCH_CHECK("k_patchify_nchw");
   return 0;
 }
 
-__global__ void k_patchify_nhwc(const float* __restrict__ in, float* __restrict__ A, __nv_bfloat16* __restrict__ A16, int lda,
-                                int C, size_t total) {
+__global__ void k_patchify_nhwc(const float* __restrict__ in, float* __restrict__ A, Out16 A16, int lda, int C, size_t total) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = i % C; size_t row = i / C;          // row = (b*32 + h)*32 + w
@@ -233,10 +250,10 @@ __global__ void k_patchify_nhwc(const float* __restrict__ in, float* __restrict_
   const float* p = in + ((b * 64 + 2 * h) * 64 + 2 * w) * C + c;
   store4(A, A16, row * lda + (size_t)c * 4, __ldg(p), __ldg(p + C), __ldg(p + 64 * C), __ldg(p + 65 * C));
 }
-int patchify_nhwc(const float* in, float* A, __nv_bfloat16* A16, int lda, int B, int C, cudaStream_t st) {
+int patchify_nhwc(const float* in, float* A, __nv_bfloat16* A16, __nv_bfloat16* A16_lo, int lda, int B, int C, cudaStream_t st) {
   DVD_REQUIRE(in && (A || A16) && lda % 4 == 0 && lda >= 4 * C, "patchify_nhwc: bad args");
   size_t total = (size_t)B * 1024 * C;
-  k_patchify_nhwc<<<cdiv(total, 256), 256, 0, st>>>(in, A, A16, lda, C, total);
+  k_patchify_nhwc<<<cdiv(total, 256), 256, 0, st>>>(in, A, Out16{A16, A16_lo}, lda, C, total);
   DVD_LAUNCH_CHECK("k_patchify_nhwc");
   return 0;
 }
@@ -244,7 +261,7 @@ int patchify_nhwc(const float* in, float* A, __nv_bfloat16* A16, int lda, int B,
 // ------------------------------------------------------------------------------------------ r operand (+ feature warp)
 __global__ void __launch_bounds__(256) k_build_r(const float* __restrict__ flow, const float* __restrict__ feat,
                                                  const float* __restrict__ init_feat, int init_feat_div, int mode,
-                                                 float* __restrict__ A, __nv_bfloat16* __restrict__ A16, int lda, int n_hyp) {
+                                                 float* __restrict__ A, Out16 A16, int lda, int n_hyp) {
   const int row = blockIdx.x;                  // (n*32 + h)*32 + w
   const int w = row % 32, h = (row / 32) % 32, n = row / 1024;
   const int c = threadIdx.x;                   // feature channel 0..255
@@ -284,13 +301,14 @@ __global__ void __launch_bounds__(256) k_build_r(const float* __restrict__ flow,
   // zero the K padding (lda may exceed 1032 for the tensor-core path)
   for (int k = 1032 + c; k < lda; k += 256) {
     if (A) A[(size_t)row * lda + k] = 0.f;
-    if (A16) A16[(size_t)row * lda + k] = __float2bfloat16_rn(0.f);
+    if (A16.hi) A16.hi[(size_t)row * lda + k] = __float2bfloat16_rn(0.f);
+    if (A16.lo) A16.lo[(size_t)row * lda + k] = __float2bfloat16_rn(0.f);
   }
 }
 int build_r_operand(const float* init_flow, const float* feat_nhwc, const float* init_feat_nchw, int init_feat_div, int mode,
-                    float* A, __nv_bfloat16* A16, int lda, int N, int n_hyp, cudaStream_t st) {
+                    float* A, __nv_bfloat16* A16, __nv_bfloat16* A16_lo, int lda, int N, int n_hyp, cudaStream_t st) {
   DVD_REQUIRE(init_flow && feat_nhwc && (A || A16) && lda >= 1032 && lda % 4 == 0 && n_hyp > 0 && init_feat_div > 0, "build_r: bad args");
-  k_build_r<<<N * 1024, 256, 0, st>>>(init_flow, feat_nhwc, init_feat_nchw, init_feat_div, mode, A, A16, lda, n_hyp);
+  k_build_r<<<N * 1024, 256, 0, st>>>(init_flow, feat_nhwc, init_feat_nchw, init_feat_div, mode, A, Out16{A16, A16_lo}, lda, n_hyp);
   DVD_LAUNCH_CHECK("k_build_r");
   return 0;
 }
@@ -540,7 +558,7 @@ __global__ void __launch_bounds__(256) k_dwconv(const float4* __restrict__ in, c
   }
   float4 s = __ldg(sc + c), t = __ldg(sh + c);
   float r0 = fmaxf(acc.x * s.x + t.x, 0.f), r1 = fmaxf(acc.y * s.y + t.y, 0.f), r2 = fmaxf(acc.z * s.z + t.z, 0.f), r3 = fmaxf(acc.w * s.w + t.w, 0.f);
-  store4(out, out16, i * 4, r0, r1, r2, r3);
+  store4(out, Out16{out16, nullptr}, i * 4, r0, r1, r2, r3);
 }
 // bf16 in / bf16 out variant for the tensor path: 8 channels (16 bytes) per thread, fp32 accumulation.
 // CTA = 8 x-positions (one per warp) x 256 channels (8 per lane) x a vertical strip of RS output rows.  The 9 x 256 tap weights and
@@ -549,8 +567,9 @@ __global__ void __launch_bounds__(256) k_dwconv(const float4* __restrict__ in, c
 // row of the strip loaded once and fed to up to three output rows -> (RS+2)*3 activation loads + 18 LDS.128 per RS outputs, ~80
 // registers, one wave of 512 CTAs.
 template <int RS>
-__global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ in, const float* __restrict__ w9, const float* __restrict__ sc,
-                                                     const float* __restrict__ sh, uint4* __restrict__ out, int C8) {
+__global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ in, const uint4* __restrict__ in_lo, const float* __restrict__ w9,
+                                                     const float* __restrict__ sc, const float* __restrict__ sh, uint4* __restrict__ out,
+                                                     uint4* __restrict__ out_lo, int C8) {
   __shared__ __align__(16) float s_w[9][256];
   __shared__ __align__(16) float s_sc[256], s_sh[256];
   pdl_trigger();
@@ -589,8 +608,14 @@ __global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ i
       if (yy < 0 || yy >= 32) continue;
       const uint4 v = __ldg(in + (n * 1024 + yy * 32 + xx) * C8 + c8);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-      const float f[8] = {__low2float(h[0]), __high2float(h[0]), __low2float(h[1]), __high2float(h[1]),
-                          __low2float(h[2]), __high2float(h[2]), __low2float(h[3]), __high2float(h[3])};
+      float f[8] = {__low2float(h[0]), __high2float(h[0]), __low2float(h[1]), __high2float(h[1]),
+                    __low2float(h[2]), __high2float(h[2]), __low2float(h[3]), __high2float(h[3])};
+      if (in_lo) {                                         // split pair: value = hi + lo
+        const uint4 vl = __ldg(in_lo + (n * 1024 + yy * 32 + xx) * C8 + c8);
+        const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&vl);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { f[2 * k] += __low2float(hl[k]); f[2 * k + 1] += __high2float(hl[k]); }
+      }
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int o = r + 1 - ky;                          // output row (inside the strip) that sees input row r through tap row ky
@@ -607,21 +632,20 @@ __global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ i
     const float r8[8] = {fmaxf(acc[o][0] * s0.x + t0.x, 0.f), fmaxf(acc[o][1] * s0.y + t0.y, 0.f), fmaxf(acc[o][2] * s0.z + t0.z, 0.f),
                          fmaxf(acc[o][3] * s0.w + t0.w, 0.f), fmaxf(acc[o][4] * s1.x + t1.x, 0.f), fmaxf(acc[o][5] * s1.y + t1.y, 0.f),
                          fmaxf(acc[o][6] * s1.z + t1.z, 0.f), fmaxf(acc[o][7] * s1.w + t1.w, 0.f)};
-    uint4 ov;
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(r8[0], r8[1]), p1 = __floats2bfloat162_rn(r8[2], r8[3]);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(r8[4], r8[5]), p3 = __floats2bfloat162_rn(r8[6], r8[7]);
-    ov.x = *reinterpret_cast<uint32_t*>(&p0); ov.y = *reinterpret_cast<uint32_t*>(&p1);
-    ov.z = *reinterpret_cast<uint32_t*>(&p2); ov.w = *reinterpret_cast<uint32_t*>(&p3);
+    uint4 ov, ol;
+    split_bf16x2(r8[0], r8[1], ov.x, ol.x); split_bf16x2(r8[2], r8[3], ov.y, ol.y);
+    split_bf16x2(r8[4], r8[5], ov.z, ol.z); split_bf16x2(r8[6], r8[7], ov.w, ol.w);
     out[(n * 1024 + (size_t)(y0 + o) * 32 + x) * C8 + c8] = ov;
+    if (out_lo) out_lo[(n * 1024 + (size_t)(y0 + o) * 32 + x) * C8 + c8] = ol;
   }
 }
-int dwconv3x3_bn_relu_bf16(const __nv_bfloat16* in, const float* w9c, const float* scale, const float* shift, __nv_bfloat16* out, int N, int C,
-                           cudaStream_t st) {
+int dwconv3x3_bn_relu_bf16(const __nv_bfloat16* in, const __nv_bfloat16* in_lo, const float* w9c, const float* scale, const float* shift,
+                           __nv_bfloat16* out, __nv_bfloat16* out_lo, int N, int C, cudaStream_t st) {
   DVD_REQUIRE(in && w9c && scale && shift && out && C % 8 == 0, "dwconv_bf16: bad args");
   constexpr int RS = 4;
   DVD_REQUIRE((long long)N * (32 / RS) <= 65535, "dwconv_bf16: batch too large for the grid");
-  DVD_CUDA(launch_pdl(8, k_dwconv_bf16<RS>, dim3(cdiv(C / 8, 32), 4, N * (32 / RS)), dim3(256), (size_t)0, st, (const uint4*)in, w9c, scale, shift,
-                      (uint4*)out, C / 8));
+  DVD_CUDA(launch_pdl(8, k_dwconv_bf16<RS>, dim3(cdiv(C / 8, 32), 4, N * (32 / RS)), dim3(256), (size_t)0, st, (const uint4*)in, (const uint4*)in_lo, w9c, scale,
+                      shift, (uint4*)out, (uint4*)out_lo, C / 8));
   DVD_LAUNCH_CHECK("k_dwconv_bf16");
   return 0;
 }
@@ -739,6 +763,40 @@ __global__ void k_f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __res
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st) {
   k_f32_to_bf16<<<cdiv(n, 256), 256, 0, st>>>(in, out, n);
   DVD_LAUNCH_CHECK("k_f32_to_bf16");
+  return 0;
+}
+
+// fp32 -> split pair hi = bf16(v), lo = bf16(v - hi)   (test hooks; the product path splits in the producing epilogues)
+__global__ void k_f32_split_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = in[i];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+int f32_split_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t st) {
+  k_f32_split_bf16<<<cdiv(n, 256), 256, 0, st>>>(in, hi, lo, n);
+  DVD_LAUNCH_CHECK("k_f32_split_bf16");
+  return 0;
+}
+__global__ void k_f32_to_f16(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+int f32_to_f16(const float* in, void* out, long long n, cudaStream_t st) {
+  k_f32_to_f16<<<cdiv(n, 256), 256, 0, st>>>(in, (__half*)out, n);
+  DVD_LAUNCH_CHECK("k_f32_to_f16");
+  return 0;
+}
+// out = hi (+ lo)
+__global__ void k_pair_to_f32(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(hi[i]) + (lo ? __bfloat162float(lo[i]) : 0.f);
+}
+int pair_to_f32(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, long long n, cudaStream_t st) {
+  k_pair_to_f32<<<cdiv(n, 256), 256, 0, st>>>(hi, lo, out, n);
+  DVD_LAUNCH_CHECK("k_pair_to_f32");
   return 0;
 }
 

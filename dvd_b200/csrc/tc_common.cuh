@@ -139,9 +139,12 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, dense
+// kind::f16 instruction descriptor: D fp32 (bit 4), A/B format (bits 7-9 / 10-12: 0 = fp16, 1 = bf16), both K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace tc
@@ -149,6 +152,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // ---------------------------------------------------------------------------------------- host: tensor maps
 // 2-D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols], SWIZZLE_128B
 // (box_cols * 2 bytes must be 128).  Returns 0 or a DVD_E_* code.
+// (bf16 and fp16 tiles are the same to TMA: 16-bit elements)
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                       uint32_t box_cols);
 

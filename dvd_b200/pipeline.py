@@ -21,8 +21,9 @@ from .unwarp import AFFINE
 
 class DewarpPipeline:
     def __init__(self, model: DiT, diffusion_steps: int = 3, n_batch: int = 2, docs: int = 1, height: int = 1500, width: int = 2000,
-                 noise_schedule: str = "cosine"):
+                 noise_schedule: str = "cosine", precision: str | None = None):
         self.model, self.docs, self.n_batch, self.H, self.W = model, docs, n_batch, height, width
+        self.precision = precision or model.precision
         self.dev = model.device
         if self.dev.type != "cuda":
             raise RuntimeError("DewarpPipeline needs the model on a CUDA device (no CPU path)")
@@ -30,9 +31,7 @@ class DewarpPipeline:
                                                    rescale_timesteps=True, rescale_learned_sigmas=True, timestep_respacing="")
         self.lib = _lib.lib()
         with torch.cuda.device(self.dev):
-            self.eng = model.engine(docs, n_batch)
-            self.t_scaled, t_emb, self.a, self.b = self.diffusion._plan()
-            self.tables = self.eng.tables(t_emb)
+            self._bind_engine()
             z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=self.dev)
             self.buf = {"y512": z(docs, 3, 512, 512), "mask_cat": z(docs, 1, 512, 512), "mask_y512": z(docs, 384, 64, 64),
                         "line_msk": z(docs, 64, 64, 64), "x_T": z(docs * n_batch, 2, 64, 64),
@@ -44,9 +43,24 @@ class DewarpPipeline:
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.buf.values())
         self.d2h_bytes = self.out_u8.numel()
         self.use_graph = os.environ.get("DVD_NO_GRAPH", "0") != "1"
-        self._graphs = {}                  # input-pointer tuple -> (CUDAGraph, kernels per replay, keep-alive dict)
         self.kernel_launches = 0           # kernels of libdvd_b200 launched (or replayed) through this pipeline
         self._slots = None                 # double-buffered host I/O state (submit_host / wait)
+
+    def _bind_engine(self):
+        """(Re)binds the engine, conditioning tables and graphs to the model's CURRENT packed weights: load_state_dict() / .to()
+        on the model replace them, and a pipeline that kept serving the old ones would silently use stale weights."""
+        self.eng = self.model.engine(self.docs, self.n_batch, self.precision)
+        self._packed = self.eng.packed
+        self.t_scaled, t_emb, self.a, self.b = self.diffusion._plan()
+        self.tables = self.eng.tables(t_emb)
+        self._graphs = {}
+
+    def _check_weights(self):
+        if self.model.device != self.dev:
+            raise RuntimeError("DewarpPipeline: the model was moved to another device; build a new pipeline")
+        if self.model.packed() is not self._packed:
+            with torch.cuda.device(self.dev):
+                self._bind_engine()
 
     # ---- device-resident inputs: dict with y512, mask_cat, mask_y512, line_msk, x_T, photo_u8 (all on self.dev)
     def _enqueue_sampling(self, d: dict):
@@ -90,6 +104,7 @@ class DewarpPipeline:
     def run_device(self, d: dict) -> torch.Tensor:
         """The ~230 kernel launches of one batch are captured once per set of input buffers into two CUDA graphs (sampling,
         unwarp) and replayed (the library never allocates or synchronises, so every entry point is capturable)."""
+        self._check_weights()
         with torch.cuda.device(self.dev):
             self._run("sampling", d, self.SAMPLING_KEYS, self._enqueue_sampling)
             self._run("unwarp", d, ("photo_u8",), self._enqueue_unwarp)
@@ -114,6 +129,7 @@ class DewarpPipeline:
         """Enqueue one batch (pinned host inputs) without waiting for it; returns a ticket for `wait`.  At most two batches may be
         outstanding (a ticket must be waited for before the second-next submit).  The photo is only needed by the last kernel, so
         its upload also runs underneath this batch's own sampling."""
+        self._check_weights()
         with torch.cuda.device(self.dev):
             if self._slots is None:
                 self._make_slots()
@@ -185,12 +201,16 @@ class DewarpPipeline:
                      "other": 1.0 - sum(tot_ms) / tot, "denoiser_ms_per_step": tot / n}
             gemm_tf = fl[0] / (tot_ms[0] / n * 1e-3) / 1e12 if tot_ms[0] > 0 else 0.0
             attn_tf = fl[1] / (tot_ms[1] / n * 1e-3) / 1e12 if tot_ms[1] > 0 else 0.0
-            tensor_mode = self.model.precision == "bf16"
+            tensor_mode = self.precision in ("bf16", "bf16x3")
+            passes = 3 if self.precision == "bf16x3" else 1
             peak_tf = peaks["bf16_tflops_sustained"] if tensor_mode else 72.0      # fp32 FFMA: 148 SM x 128 FMA x 2 x 1.9 GHz
-            roof = {"kernel": "dense GEMM (all linear layers of one step batch)", "bound": "tensor", "achieved": gemm_tf,
+            roof = {"kernel": "k_gemm_pair: dense GEMM (all linear layers of one step batch)", "bound": "tensor", "achieved": gemm_tf,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": None,
                     "launches_per_step": int(ln[0]), "gflop_per_step": fl[0] / 1e9, "attention_tflops": attn_tf,
                     "attention_gflop_per_step": fl[1] / 1e9,
+                    # achieved / frac count ALGORITHMIC flops (2 M N K).  The split-precision mode executes three tensor-core passes per
+                    # k-step to be fp32-accurate, so its tensor pipe does `mma_passes` x that work: frac_executed is the pipe's own load.
+                    "mma_passes": passes, "executed_tflops": gemm_tf * passes, "frac_executed": gemm_tf * passes / peak_tf,
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % which) if tensor_mode else "nominal fp32 FFMA"}
             # unwarp: fp32 contract (24 B/px) and the uint8 variant actually used end to end (6 B/px).  20 launches replayed from one
             # CUDA graph (no host time between launches) over rotating buffer pairs whose total exceeds the L2, so every launch

@@ -79,7 +79,6 @@ class SpacedDiffusion:
         self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
         self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
         self.settings = None                                                   # val_TDiff.py:52 sets it
-        self._graphs = {}
 
     # ---- per-step scalars
     def scaled_t(self, i: int) -> float:
@@ -137,16 +136,13 @@ class SpacedDiffusion:
             eng = model.engine(docs, n_batch)
             eng.static_forward(f(kw["y512"]), f(kw["mask_cat"]), f(kw["mask_y512"]), f(kw["line_msk"]))
             t_scaled, t_emb, a, b = self._plan()
-            key = (id(model), model.precision)
-            if key not in self._graphs:
-                self._graphs = {key: eng.tables(t_emb)}
-            tables = self._graphs[key]
+            tables = eng.tables(t_emb)                    # cached on the packed weights (dropped by load_state_dict / .to())
             init_feat0 = kw.get("init_feat")
             if init_feat0 is not None and (t_scaled[0] > 600 or not bool(torch.any(init_feat0 != 0))):
                 init_feat0 = None
             out = torch.empty((docs, 2, 64, 64), dtype=torch.float32, device=dev)
             eng.sample(x_T, f(kw["init_flow"]), tables, t_scaled, a, b, None if init_feat0 is None else f(init_feat0), out)
-            feat = eng.feat_nhwc().permute(0, 3, 1, 2)
+            feat = eng.feat_nhwc().permute(0, 3, 1, 2).clone()    # detached from the workspace the next call overwrites
         final = {"sample": out, "pred_xstart": out, "feat_dict": feat}
         return out, final
 

@@ -48,6 +48,13 @@ def required_keys():
     return ks
 
 
+def split_bf16(w: torch.Tensor):
+    """fp32 -> (hi, lo) bf16 pair with hi = bf16(w), lo = bf16(w - hi): the operands of the 3-pass split-precision GEMM."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
 class PackedWeights:
     """Owns the packed device tensors and the ``dvd_weights_t`` table that points into them."""
 
@@ -56,6 +63,7 @@ class PackedWeights:
         self.keep = []                      # keeps every packed tensor alive
         self.table = _lib.Weights()
         self.with_bf16 = with_bf16
+        self.tables_cache = {}              # conditioning tables per step plan: they depend on these weights and die with them
         missing = [k for k in required_keys() if k not in sd]
         if missing:
             raise KeyError(f"state_dict is missing {len(missing)} live keys, e.g. {missing[:4]}")
@@ -76,9 +84,9 @@ class PackedWeights:
         m.f32 = w.data_ptr()
         m.n, m.k = int(w.shape[0]), int(w.shape[1])
         if bf16 and self.with_bf16:
-            h = w.to(torch.bfloat16).contiguous()
-            self.keep.append(h)
-            m.bf16 = h.data_ptr()
+            h, l = split_bf16(w)
+            self.keep += [h, l]
+            m.bf16, m.bf16_lo = h.data_ptr(), l.data_ptr()
         return m
 
     def _bn(self, sd, prefix):
@@ -94,10 +102,11 @@ class PackedWeights:
             w = sd[p + ".weight"].float()                                  # [Cout, Cin, 3, 3] -> [Cout, ky, kx, Cin]
             T.pyr[i] = self._mat(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), bf16=(i > 0))
             if i == 0 and self.with_bf16:                                   # level_0: K = 36 zero-padded to 64 for the tcgen05 im2col GEMM
-                pad = torch.zeros((w.shape[0], 64), dtype=torch.bfloat16, device=self.device)
-                pad[:, :36] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(self.device).to(torch.bfloat16)
-                self.keep.append(pad)
-                T.pyr[0].bf16 = pad.data_ptr()
+                pad = torch.zeros((w.shape[0], 64), dtype=torch.float32, device=self.device)
+                pad[:, :36] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(self.device)
+                h, l = split_bf16(pad)
+                self.keep += [h, l]
+                T.pyr[0].bf16, T.pyr[0].bf16_lo = h.data_ptr(), l.data_ptr()
             T.pyr_b[i] = self._vec(sd[p + ".bias"])
         for i, e in enumerate(EMB_KEYS):
             w = sd[f"{e}_embedder.proj.weight"].float()

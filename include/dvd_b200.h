@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DVD_ABI_VERSION 1
+#define DVD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DVD_API __attribute__((visibility("default")))
@@ -45,12 +45,15 @@ extern "C" {
 
 /* precision of the denoiser's dense contractions */
 #define DVD_PREC_FP32  0      /* fp32 FFMA reference mode (bit-for-bit reproducible)   */
-#define DVD_PREC_BF16  1      /* bf16 operands, fp32 accumulate on tcgen05 / TMEM      */
+#define DVD_PREC_BF16  1      /* bf16 operands, fp32 accumulate on tcgen05 / TMEM (fast, reduced accuracy)        */
+#define DVD_PREC_BF16X3 2     /* fp32-accurate tensor-core mode: every GEMM operand is a bf16 pair hi+lo and runs */
+                              /* three tcgen05 passes (hi*hi + lo*hi + hi*lo, error ~2^-16); attention in fp16     */
 
 /* One dense weight matrix W[n][k] (row-major, K contiguous == torch Linear layout). */
 typedef struct dvd_mat {
   const float* f32;           /* always present                                       */
-  const void*  bf16;          /* bf16 copy for DVD_PREC_BF16 (may be NULL in fp32)    */
+  const void*  bf16;          /* bf16(W) for the tensor modes (may be NULL in fp32)    */
+  const void*  bf16_lo;       /* bf16(W - bf16(W)) for DVD_PREC_BF16X3 (else NULL)     */
   int32_t n, k;
 } dvd_mat_t;
 
@@ -121,6 +124,9 @@ DVD_API int dvd_fullres_grid_f32(const float* map, float* grid, int B, int H, in
 
 /* ---- denoiser + sampler ------------------------------------------------------------------- */
 DVD_API size_t dvd_workspace_bytes(int docs, int n_hyp, int precision);
+/* Once after allocating a workspace (and before its first use): zeroes the split-K tile counters of the persistent GEMM,
+ * which every later launch leaves at zero again. */
+DVD_API int dvd_workspace_init(void* workspace, size_t workspace_bytes, int docs, int n_hyp, int precision, void* stream);
 
 /* CM:97-139 + CM:209-211 + CM:331: conditioning tables for `n_steps` scalar timesteps
  * (values AFTER the CM:575-579 remap).  tables [n_steps][DVD_TABLE_ROW]. */
@@ -169,15 +175,22 @@ DVD_API const float* dvd_workspace_feat(void* workspace, int docs, int n_hyp, in
 DVD_API const float* dvd_workspace_tensor(void* workspace, int docs, int n_hyp, int precision, const char* name,
                                           long long* numel);
 
+/* test hook: make dvd_denoise_step (of the calling thread) return after a stage so that its output can be read with
+ * dvd_workspace_tensor("X"): 0 = off, 1 = DiT block (X = x1|x2|x3|x4, CM:623), 2 = adaptive positional encoding (CA:143-157),
+ * 3 + l = decoder layer l (CA:377-396). */
+DVD_API int dvd_debug_stop_after(int stage);
+
 /* ---- building blocks exported for parity tests (not needed by the reference-side binding) ---- */
 DVD_API int dvd_test_gemm(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                   int precision, void* scratch, size_t scratch_bytes, void* stream);
 DVD_API int dvd_test_attention(const float* q, const float* k, const float* v, float* o, int batch, int heads,
                        int T, int d, float scale, int precision, void* scratch, size_t scratch_bytes,
                        void* stream);
-/* Plain tensor-core GEMM (tuning / micro-benchmarks): out = A[M,K] W[N,K]^T + bias; bf16 operands, bf16 and/or fp32 output. */
-DVD_API int dvd_gemm_bf16(const void* A16, int lda, const void* W16, int ldw, const float* bias, void* out16, float* out32,
-                          int M, int N, int K, void* stream);
+/* Plain tensor-core GEMM (tuning / micro-benchmarks): out = A[M,K] W[N,K]^T + bias; bf16 operands (A16_lo / W16_lo non-NULL:
+ * split pairs, three passes), bf16 and/or fp32 output.  splitk_scratch: optional zero-initialised 3*M*N*4 + 16 KB bytes. */
+DVD_API int dvd_gemm_bf16(const void* A16, const void* A16_lo, int lda, const void* W16, const void* W16_lo, int ldw,
+                          const float* bias, void* out16, float* out32, int M, int N, int K, void* splitk_scratch,
+                          size_t splitk_bytes, void* stream);
 /* Kernel-class profiler: between begin/end every dense contraction launched by this thread is bracketed by CUDA
  * events.  end() synchronises and returns, for the classes {0: GEMM, 1: attention, 2: pyramid conv}, the summed
  * device time (ms), algorithmic FLOPs and launch counts. */

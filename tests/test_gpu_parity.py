@@ -1,10 +1,13 @@
 """GPU parity tests: the CUDA path (through the C-ABI library) against the CPU oracle and the golden
 fixtures produced by the unmodified reference.  Run on the B200 box with ``-m gpu``.
 
-Tolerances (north_star): final backward map within 0.05 px mean / 0.5 px max in fp32 mode, i.e.
-2.48e-5 / 2.48e-4 in normalised units at the largest named size (4032 px: px = d * (4032-1)/2);
-bf16 mode: <= 1.5e-3 mean / 6e-3 max normalised (the reference itself moves by
-9.5e-4 / 2.7e-3 when its GEMM operands are rounded to bf16); unwarped image PSNR >= 45 dB.
+Tolerances (north_star): final backward map within 0.05 px mean / 0.5 px max, i.e. 2.48e-5 / 2.48e-4 in
+normalised units at the largest named size (4032 px: px = d * (4032-1)/2), and unwarped image PSNR >= 45 dB
+at 1500x2000 and 4032x3024.  Both gates are asserted for the two modes that claim them: ``fp32`` (FFMA) and
+``bf16x3`` (tensor cores, split-precision operands: the default / benchmarked mode).  The single-pass ``bf16``
+mode is the stated reduced-accuracy mode: <= 1.5e-3 mean / 6e-3 max normalised (the
+reference itself moves by 9.5e-4 / 2.7e-3 when its GEMM operands are rounded to bf16); its image PSNR is
+measured and asserted against that looser bound only (>= 20 dB), it does NOT meet the 45 dB gate.
 """
 import ctypes as C
 import os
@@ -34,7 +37,7 @@ def dev():
 def models(dev, state_dict_live):
     from dvd_b200.model import DiT
     out = {}
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "bf16", "bf16x3"):
         m = DiT(precision=prec)
         m.load_state_dict(state_dict_live, strict=False)
         out[prec] = m.to(dev).eval()
@@ -231,7 +234,7 @@ def _run_gemm(dev, M, N, K, prec):
     A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
     Ad, Wd, bd = A.to(dev), W.to(dev), b.to(dev)
     Cd = torch.empty(M, N, device=dev)
-    scratch = torch.empty((M + N) * K * 2 + 1024, dtype=torch.uint8, device=dev)
+    scratch = torch.zeros((M + N) * K * 4 + 3 * M * N * 4 + (64 << 10), dtype=torch.uint8, device=dev)   # operands (+ lo) + split-K state
     _lib.check(_lib.lib().dvd_test_gemm(_lib.ptr(Ad), _lib.ptr(Wd), _lib.ptr(bd), _lib.ptr(Cd), M, N, K, prec, _lib.ptr(scratch),
                                         scratch.numel(), _lib.stream_ptr()), "dvd_test_gemm")
     torch.cuda.synchronize()
@@ -253,6 +256,17 @@ def test_gemm_bf16_tcgen05(dev, M, N, K):
     assert float((Cg - ref).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 1032), (2048, 1536, 1536), (8192, 1152, 384), (2048, 4608, 1536),
+                                   (8192, 384, 1536), (2048, 1536, 2048), (2048, 2048, 1536), (512, 64, 64), (384, 192, 128)])
+def test_gemm_bf16x3_tcgen05(dev, M, N, K):
+    """Split-precision GEMM (three tcgen05 passes): fp32-accurate.  Covers the persistent CTA-pair kernel with and without split-K
+    (the M = 2048 decoder shapes), every tile width, and the generic single-CTA kernel (M = 128 / 384)."""
+    Cg, A, W, b = _run_gemm(dev, M, N, K, 2)
+    ref = (A.double() @ W.double().t() + b.double()).float()
+    err = float((Cg - ref).abs().max()) / max(1.0, float(ref.abs().max()))
+    assert err < 4e-5, err
+
+
 def test_gemm_bf16_more_row_tiles_than_grid_y(dev):
     """M / 128 > 65535 row tiles (the 512x512 pyramid levels of >= 32 documents in flight): the tile index is folded into
     gridDim.z, with a ragged last z-slice."""
@@ -263,7 +277,8 @@ def test_gemm_bf16_more_row_tiles_than_grid_y(dev):
     W = (torch.randn(N, K, device=dev, generator=g) / K ** 0.5).bfloat16()
     b = torch.randn(N, device=dev, generator=g)
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    _lib.check(_lib.lib().dvd_gemm_bf16(_lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(b), _lib.ptr(out), None, M, N, K, _lib.stream_ptr()), "gemm")
+    _lib.check(_lib.lib().dvd_gemm_bf16(_lib.ptr(A), None, K, _lib.ptr(W), None, K, _lib.ptr(b), _lib.ptr(out), None, M, N, K, None, 0,
+                                        _lib.stream_ptr()), "gemm")
     torch.cuda.synchronize()
     for r0 in (0, 32768 * 128 - 64, 65535 * 128 - 64, 65536 * 128 - 64, M - 256):      # start, z-slice boundaries, ragged tail
         ref = A[r0:r0 + 256].float() @ W.float().t() + b
@@ -297,6 +312,14 @@ def test_attention_bf16_tcgen05(dev, d):
     assert float((o - ref).abs().max()) < 2e-2 and float((o - ref).abs().mean()) < 2e-3
 
 
+@pytest.mark.parametrize("d", [64, 256])
+def test_attention_fp16_tcgen05(dev, d):
+    """bf16x3 mode: fp16 Q / K / V^T / P on tcgen05, output as a bf16 hi + lo pair."""
+    o, q, k, v = _run_attn(dev, 2, 6, 1024, d, 2)
+    ref = O._mha_core(q.half().float(), k.half().float(), v.half().float(), 6, d ** -0.5)
+    assert float((o - ref).abs().max()) < 3e-3 and float((o - ref).abs().mean()) < 2.5e-4
+
+
 # ----------------------------------------------------------------------------------------------- denoiser stages
 def test_static_forward_and_first_step_fp32(dev, models, state_dict_live, golden_dir):
     sd, model = state_dict_live, models["fp32"]
@@ -320,6 +343,50 @@ def test_static_forward_and_first_step_fp32(dev, models, state_dict_live, golden
     np.testing.assert_allclose((eng.tensor("r").view(2, 1024, 384).cpu() - pos)[:, ::8, ::8].numpy(), st["r_embed"], atol=1e-4, rtol=1e-4)
     np.testing.assert_allclose((eng.tensor("xe").view(2, 1024, 384).cpu() - pos)[:, ::8, ::8].numpy(), st["obs_embed"], atol=1e-5, rtol=1e-4)
     assert float((pred.cpu() - torch.from_numpy(g3["pred"][0])).abs().max()) < 1e-4
+
+
+STAGE_TOL = {"fp32": 1e-4, "bf16x3": 2e-4, "bf16": 6e-2}      # max abs error against the reference's stage outputs (values are O(1..10))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16"])
+def test_block11_and_decoder_stages_match_reference(dev, models, state_dict_live, golden_dir, prec):
+    """Stage-level outputs of the first denoiser forward against hooks on the UNMODIFIED reference (oracle/make_golden.py):
+    DiT block 11 (x4,x3,x2,x1), adaptive positional encoding, decoder layer 0 and the decoder output (after decoder.layer_norm)."""
+    import torch.nn.functional as F
+    from dvd_b200 import _lib
+    sd, model = state_dict_live, models[prec]
+    inp = synth.make_doc_inputs(0, H=96, W=128)
+    st = np.load(os.path.join(golden_dir, "stages_doc0_step0.npz"))
+    eng = model.engine(1, 2)
+    g = lambda k: inp[k].to(dev).contiguous()
+    eng.static_forward(g("y512"), g("mask_cat"), g("mask_y512"), g("line_msk"))
+    tab = eng.tables([2.0])
+    pred = torch.empty(2, 2, 64, 64, device=dev)
+    tol = STAGE_TOL[prec]
+
+    def run(stage):
+        _lib.lib().dvd_debug_stop_after(stage)
+        try:
+            eng.denoise_step(inp["x_T"].to(dev), torch.zeros(2, 2, 64, 64, device=dev), None, True, tab[0], 1.0, 0.0, pred, None)
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().dvd_debug_stop_after(0)
+        return eng.tensor("X").view(2, 1024, 1536).cpu().clone()
+
+    def check(got, want, what):
+        err = float(np.abs(got - want).max())
+        assert err < tol, (what, err)
+
+    X = run(1)                                                     # x1 | x2 | x3 | x4 along the channels (cross_model.py:623)
+    blk = np.stack([X[:, ::8, (3 - j) * 384:(4 - j) * 384:8].numpy() for j in range(4)])      # golden order x4, x3, x2, x1
+    check(blk, st["block11"], "block11")
+    X = run(2)
+    check(X.transpose(1, 2).reshape(2, 1536, 32, 32)[:, ::16, ::4, ::4].numpy(), st["posenc"], "posenc")
+    X = run(3)
+    check(X[:, ::8, ::16].numpy(), st["dec_layer0"], "dec_layer0")
+    X = run(8)                                                     # after decoder layer 5
+    dec = F.layer_norm(X, (1536,), sd["decoder.layer_norm.weight"], sd["decoder.layer_norm.bias"], 1e-5)
+    check(dec[:, ::8, ::16].numpy(), st["decoder"], "decoder")
 
 
 def test_dropin_model_call_matches_reference(dev, models, golden_dir):
@@ -347,6 +414,21 @@ def test_sampling_fp32_matches_reference_golden(dev, models, golden_dir, doc):
 
 
 @pytest.mark.parametrize("doc", [0, 1])
+def test_sampling_bf16x3_meets_the_fp32_gate(dev, models, golden_dir, doc):
+    """The default tensor-core mode (split-precision GEMMs, fp16 attention) is held to the SAME map gate as fp32."""
+    g = np.load(os.path.join(golden_dir, f"sample_S3_doc{doc}.npz"))
+    out, _ = _sample(models["bf16x3"], synth.make_doc_inputs(doc, H=96, W=128))
+    d = (out - torch.from_numpy(g["sample"])).abs()
+    assert float(d.mean()) < FP32_MEAN and float(d.max()) < FP32_MAX, (float(d.mean()) * 2015.5, float(d.max()) * 2015.5)
+
+
+def test_sampling_S10_thresholds_bf16x3(dev, models, golden_dir):
+    g = np.load(os.path.join(golden_dir, "sample_S10_doc2.npz"))
+    out, _ = _sample(models["bf16x3"], synth.make_doc_inputs(2, H=96, W=128), S=10)
+    assert float((out - torch.from_numpy(g["sample"])).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("doc", [0, 1])
 def test_sampling_bf16_within_stated_bound(dev, models, golden_dir, doc):
     g = np.load(os.path.join(golden_dir, f"sample_S3_doc{doc}.npz"))
     out, _ = _sample(models["bf16"], synth.make_doc_inputs(doc, H=96, W=128))
@@ -361,7 +443,7 @@ def test_sampling_S10_thresholds_fp32(dev, models, golden_dir):
     assert float((out - torch.from_numpy(g["sample"])).abs().max()) < 2e-3
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 def test_document_batch_equals_single_documents(dev, models, prec):
     """Documents are independent: a batch of 3 documents gives the same maps as three separate calls."""
     inps = [synth.make_doc_inputs(d, with_photo=False) for d in (0, 1, 5)]
@@ -369,31 +451,7 @@ def test_document_batch_equals_single_documents(dev, models, prec):
     both, _ = _sample(models[prec], cat)
     for j, i in enumerate(inps):
         one, _ = _sample(models[prec], i)
-        assert float((both[j:j + 1] - one).abs().max()) < (1e-5 if prec == "fp32" else 1e-3)
-
-
-def test_two_chain_hypothesis_split_is_identical(dev, models, golden_dir):
-    """DVD_HYP_SPLIT=1 (the two hypotheses of a document sampled as two concurrent chains on two streams) gives the same map as
-    the batched default: compared through the reference's golden sample (the env is read once per process, hence the subprocess)."""
-    import subprocess, sys, tempfile
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = ("import sys, torch, numpy as np; sys.path.insert(0, %r)\n"
-            "from oracle import synth; from dvd_b200.model import DiT; from dvd_b200.sampler import create_gaussian_diffusion\n"
-            "m = DiT(precision='fp32'); m.load_state_dict(synth.make_state_dict(1234, live_only=True), strict=False); m = m.cuda().eval()\n"
-            "inp = {k: v.cuda() for k, v in synth.make_doc_inputs(0, H=96, W=128).items() if k != 'photo'}\n"
-            "kw = {'init_flow': inp['init_flow'], 'src_feat': None, 'src_64': None, 'y512': inp['y512'], 'tmode': 'stage_1_dit_cross',\n"
-            "      'mask_cat': inp['mask_cat'], 'init_feat': inp['init_feat'], 'iter': True, 'mask_y512': inp['mask_y512'], 'line_msk': inp['line_msk']}\n"
-            "d = create_gaussian_diffusion(steps=3, noise_schedule='cosine', predict_xstart=True, rescale_timesteps=True,\n"
-            "                              rescale_learned_sigmas=True, timestep_respacing='')\n"
-            "out, _ = d.ddim_sample_loop(m, (1, 2, 64, 64), clip_denoised=False, model_kwargs=kw, eta=0.0, n_batch=2, time_variant=True, x_T=inp['x_T'])\n"
-            "torch.cuda.synchronize(); np.save(sys.argv[1], out.cpu().numpy())\n" % root)
-    with tempfile.TemporaryDirectory() as td:
-        f = os.path.join(td, "split.npy")
-        subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, DVD_HYP_SPLIT="1"), timeout=600)
-        split = np.load(f)
-    g = np.load(os.path.join(golden_dir, "sample_S3_doc0.npz"))
-    d = np.abs(split - g["sample"])
-    assert float(d.mean()) < FP32_MEAN and float(d.max()) < FP32_MAX, (float(d.mean()), float(d.max()))
+        assert float((both[j:j + 1] - one).abs().max()) < {"fp32": 1e-5, "bf16x3": 1e-5, "bf16": 1e-3}[prec]
 
 
 def test_pipeline_device_host_and_pipelined_submission_agree(dev, models):
@@ -445,34 +503,53 @@ def test_seeded_noise_consumption_matches_reference_order(dev, models):
     assert torch.equal(a, b)
 
 
-def test_end_to_end_dewarp_psnr(dev, models, golden_dir):
-    """Sampling (fp32 mode) + unwarp of a 1500x2000 photo vs oracle unwarp of the reference's golden map: PSNR >= 45 dB."""
+@pytest.mark.parametrize("H,W", [(1500, 2000), (4032, 3024)])
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_end_to_end_dewarp_psnr(dev, models, golden_dir, prec, H, W):
+    """Sampling + unwarp of a full-size photo vs the oracle's unwarp of the reference's golden map: PSNR >= 45 dB (north_star),
+    for the FFMA mode and for the default tensor-core mode, at both BASELINE photo sizes (fp32 image and truncated uint8)."""
     from dvd_b200 import dewarp_fullres
     g = np.load(os.path.join(golden_dir, "sample_S3_doc0.npz"))
     inp = synth.make_doc_inputs(0, H=96, W=128)
-    out, _ = _sample(models["fp32"], inp)
-    photo = synth.make_photo(1500, 2000, 77, "page")
+    out, _ = _sample(models[prec], inp)
+    photo = synth.make_photo(H, W, 77, "page")
     img = dewarp_fullres(out.to(dev), photo.to(dev)).cpu()
     ref = O.unwarp(torch.from_numpy(g["sample"]), photo)
     assert psnr(img, ref) >= 45.0, psnr(img, ref)
+    img8 = dewarp_fullres(out.to(dev), photo.permute(0, 2, 3, 1).to(torch.uint8).contiguous().to(dev)).cpu()
+    ref8 = torch.from_numpy(O.to_uint8_hwc(ref)).unsqueeze(0)
+    assert psnr(img8.float(), ref8.float()) >= 45.0, psnr(img8.float(), ref8.float())
+
+
+def test_bf16_mode_image_error_is_reported_not_gated(dev, models, golden_dir, capsys):
+    """Single-pass bf16 is the stated reduced-accuracy mode: its image PSNR at 1500x2000 is measured here (and printed) and only held
+    to the looser stated bound; it is below north_star's 45 dB, which is why bf16x3 is the default and benchmarked mode."""
+    from dvd_b200 import dewarp_fullres
+    g = np.load(os.path.join(golden_dir, "sample_S3_doc0.npz"))
+    out, _ = _sample(models["bf16"], synth.make_doc_inputs(0, H=96, W=128))
+    photo = synth.make_photo(1500, 2000, 77, "page")
+    p = psnr(dewarp_fullres(out.to(dev), photo.to(dev)).cpu(), O.unwarp(torch.from_numpy(g["sample"]), photo))
+    with capsys.disabled():
+        print(f"\n[bf16 single-pass] image PSNR at 1500x2000 vs reference map: {p:.1f} dB (gate for fp32 / bf16x3: 45 dB)")
+    assert p >= 20.0, p
 
 
 # ----------------------------------------------------------------------------------------------- kernel variants and the evaluation drop-in
-@pytest.mark.parametrize("env", [{"DVD_GEMM_V1": "1"}, {"DVD_GEMM_V2": "1"}, {"DVD_GEMM_V3": "1"}, {"DVD_GEMM_V1": "1", "DVD_GEMM_CLUSTER": "22"},
-                                 {"DVD_GEMM_V1": "1", "DVD_GEMM_CLUSTER": "12"}, {"DVD_GEMM_V1": "1", "DVD_GEMM_CLUSTER": "21"}])
+@pytest.mark.parametrize("env", [{"DVD_GEMM_V1": "1"}, {}, {"DVD_GEMM_SPLITS": "2"}, {"DVD_GEMM_SPLITS": "4"}, {"DVD_GEMM_BN": "128"},
+                                 {"DVD_GEMM_BN": "192"}, {"DVD_GEMM_BN": "64", "DVD_GEMM_SPLITS": "3"}])
 def test_gemm_kernel_variants_agree(dev, env):
-    """The tcgen05 GEMM kernels (two CTAs/SM with or without TMA-multicast clusters of shape 2x2 / 1x2 / 2x1, persistent
-    double-buffered, CTA-pair cta_group::2) are selected by shape at run time; force each one (env is read once per process, hence
-    the subprocess) over the denoiser's shapes."""
+    """The tcgen05 GEMM kernels (generic single-CTA; persistent CTA-pair with every tile width and split-K factor) are selected by
+    shape at run time; force each configuration (env is read once per process, hence the subprocess) over the denoiser's shapes in
+    both tensor modes."""
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "gemm_bench.py")], env={**os.environ, **env}, capture_output=True,
-                         text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "gemm_bench.py"), "--check"], env={**os.environ, **env},
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if "relerr" in l]
-    assert len(lines) >= 8
+    assert len(lines) >= 16
     for l in lines:
-        assert float(l.split("relerr")[1]) < 1e-2, l
+        assert float(l.split("relerr")[1]) < (1e-2 if " bf16 " in l else 4e-5), l
 
 
 def test_run_evaluation_docunet_dropin(dev, models, golden_dir, tmp_path, monkeypatch):
