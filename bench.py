@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 10 --warmup 3                  # our arm, N=1
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W    # N>1 (document-sharded, no collective)
-    python bench.py --impl reference ...                             # reference's CPU path (oracle port)
+    python bench.py --impl reference ...                             # the UNMODIFIED reference on the host CPU (baseline/_ref)
 
 One "step" = one batch of `--docs` synthetic documents per GPU through the whole hot path:
 static conditioning (pyramid, embeds) -> S-step DDIM sampling (n_batch hypotheses) -> hypothesis
@@ -13,11 +13,18 @@ configs[1] (val_TDiff batch 1, 2000x1500 photo, S=3, n_batch=2).
   value : docs/s with the inputs already resident in HBM
   e2e   : the same through the public API with pinned-host inputs (H2D inside the timed region)
           and the unwarped uint8 image read back to the host (D2H inside the timed region)
+Precision: the timed mode is `bf16x3` (tensor cores, split-precision operands, fp32-accurate: the mode that meets every
+accuracy gate); the single-pass `bf16` mode and the FFMA `fp32` mode are measured beside it (N=1) as `bf16_mode` / `fp32_mode`.
+Baselines reported beside the number (rank 0, N=1, after the timed region): `cpu_baseline` (one document through the reference
+on the host cores, which also yields the `parity` object: our output against the reference's on the same document),
+`torch_b200` (the reference's own modules on this GPU, TF32 off / on) and `preprocessing_ms` (the reference's three
+preprocessing networks on this GPU, timed separately as north_star asks).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -39,17 +46,27 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DVD_PRECISION", "bf16x3"), choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--docs", type=int, default=1, help="documents per step per GPU")
+    ap.add_argument("--total-docs", type=int, default=0, help="strong scaling: this many documents per step over ALL GPUs (BASELINE configs[2])")
     ap.add_argument("--height", type=int, default=1500)
     ap.add_argument("--width", type=int, default=2000)
     ap.add_argument("--diffusion-steps", type=int, default=3)
     ap.add_argument("--n-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip bf16_mode / fp32_mode / torch_b200 / preprocessing / drop-in API legs")
     return ap.parse_args()
 
 
 def workload_name(a):
     return (f"val_TDiff batch {a.docs}/GPU: S={a.diffusion_steps} DDIM steps x n_batch={a.n_batch} hypotheses + unwarp of a "
             f"{a.width}x{a.height} (WxH) synthetic photo")
+
+
+def config_dict(a):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": workload_name(a), "docs_per_step_per_gpu": a.docs, "photo_hw": [a.height, a.width],
+            "diffusion_steps": a.diffusion_steps, "n_batch": a.n_batch, "weights": "random-init (synth_workload.py seed 1234)",
+            "l2": "GPU arm: 256 MiB flush write between timed iterations (value, synchronous e2e); pipelined e2e and the CPU arm stream a new "
+                  "document every step"}
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -109,64 +126,140 @@ def algorithmic_gflop_per_doc(S, n_batch):
     return 101.87 + n_batch * S * 262.52
 
 
-# ------------------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_reference_doc_seconds(a, sd, inp, photo, full: bool):
-    """The reference's own CPU implementation of the path, as written (12 DiT blocks, nothing hoisted), via the oracle
-    port.  A bounded sample: ONE of the S denoiser forwards (n_batch hypotheses) is executed and scaled by S, plus the
-    full-resolution upsample+grid_sample+uint8 cast.  Returns seconds per document."""
-    from oracle import dvd_oracle as O
-    n = a.n_batch
-    rep = lambda v: v.repeat(n, 1, 1, 1)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        if full:
-            m = O.sample(sd, inp, S=a.diffusion_steps, n_batch=n, as_written=True)
-            t_den = time.perf_counter() - t0
-        else:
-            sch = O.Schedule(a.diffusion_steps)
-            pred, _ = O.denoiser_forward(sd, inp["x_T"], sch.scaled_t(a.diffusion_steps - 1), rep(inp["init_flow"]), rep(inp["init_feat"]),
-                                         None, y512=rep(inp["y512"]), mask_cat=rep(inp["mask_cat"]), mask_y512=rep(inp["mask_y512"]),
-                                         line_msk=rep(inp["line_msk"]), as_written=True)
-            t_den = (time.perf_counter() - t0) * a.diffusion_steps
-            m = torch.clamp(pred.mean(0, keepdim=True), -1, 1)
-        t1 = time.perf_counter()
-        img = O.unwarp(m, photo)
-        _ = O.to_uint8_hwc(img)
-        t_unw = time.perf_counter() - t1
-    return t_den + t_unw, t_den, t_unw
+def psnr_db(a: torch.Tensor, b: torch.Tensor) -> float:
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return 99.0 if mse == 0 else 10 * math.log10(255.0 ** 2 / mse)
+
+
+# ------------------------------------------------------------------------------------------------ reference legs (host CPU / stock torch)
+class ReferenceRunner:
+    """One whole document per call through the reference's own implementation of the path, as written (12 DiT blocks, nothing
+    hoisted, its debug PNG dumps): evaluation.py:80-138 + :300-306 + visualization_utils.py:75-77.
+    kind = "reference": the UNMODIFIED reference imported from baseline/_ref (or /root/reference) through oracle/ref_shims;
+    kind = "port": the oracle's restatement, only when the reference tree is absent."""
+
+    def __init__(self, a, device="cpu"):
+        import synth_workload as synth
+        self.a, self.synth, self.device = a, synth, device
+        self.sd = synth.make_state_dict(1234)
+        self.kind = "port"
+        try:
+            from oracle import ref_harness as RH
+            if RH.available():
+                self.RH = RH
+                self.model = RH.build_reference_model(self.sd).to(device)
+                self.kind = "reference"
+        except Exception as e:                                   # noqa: BLE001 - fall back to the port, say why
+            self.why = repr(e)[:200]
+
+    def doc(self, doc_id: int):
+        """-> (uint8 HWC image, map64 [1,2,64,64] on the CPU, seconds)."""
+        a = self.a
+        inp = self.synth.make_doc_inputs(doc_id, H=a.height, W=a.width)
+        photo = inp.pop("photo")
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if self.kind == "reference":
+                dev = torch.device(self.device)
+                inp_d = {k: v.to(dev) for k, v in inp.items()}
+                sample, _ = self.RH.reference_sample(self.model, inp_d, S=a.diffusion_steps, n_batch=a.n_batch, seed=2000 + doc_id)
+                _, img = self.RH.reference_unwarp(sample, photo.to(dev))
+                out = img[0].permute(1, 2, 0).cpu().numpy().astype("uint8")
+                m = sample.cpu()
+            else:
+                from oracle import dvd_oracle as O
+                m = O.sample(self.sd, inp, S=a.diffusion_steps, n_batch=a.n_batch, as_written=True)
+                out = O.to_uint8_hwc(O.unwarp(m, photo))
+        if self.device != "cpu":
+            torch.cuda.synchronize()
+        return out, m, time.perf_counter() - t0
 
 
 def run_reference(a):
+    """--impl reference: K whole documents (after W warm-up documents) through the reference on ALL host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import synth_workload as synth
     torch.set_num_threads(os.cpu_count())
-    sd = synth.make_state_dict(1234)
-    inp = synth.make_doc_inputs(0, H=a.height, W=a.width)
-    photo = inp.pop("photo")
-    for _ in range(min(a.warmup, 1)):
-        cpu_reference_doc_seconds(a, sd, inp, photo, full=False)
-    ts = [cpu_reference_doc_seconds(a, sd, inp, photo, full=False)[0] for _ in range(a.steps)]
+    r = ReferenceRunner(a)
+    for i in range(a.warmup):
+        r.doc(i)
+    ts = [r.doc(a.warmup + i)[2] for i in range(a.steps)]
     sec = sum(ts) / len(ts)
-    value = 1.0 / sec
+    value = a.docs / sec
     line = {"impl": "reference", "metric": "dewarped docs/sec (sampling+unwarp)", "value": value, "unit": "docs/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "device": "host CPU"},
-            "cpu_baseline": {"value": value, "unit": "docs/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "oracle port of the reference as written (12 DiT blocks, no hoisting); per step: 1 of the "
-                                       f"{a.diffusion_steps} denoiser forwards x{a.diffusion_steps} + full-size unwarp"},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(a),
+            "p50_latency_ms": statistics.median(ts) * 1e3,
+            "cpu_baseline": {"value": value, "unit": "docs/s", "cores": torch.get_num_threads(), "kind": r.kind,
+                             "sample": "every step = ONE WHOLE document through the reference as written (S x n_batch denoiser forwards with all 12 "
+                                       "DiT blocks, its debug PNG dumps, full-size upsample + grid_sample + uint8 cast); no extrapolation"},
             "e2e": {"value": value, "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def torch_b200_leg(a, dev):
+    """The reference's own modules on this GPU (stock cuDNN / cuBLAS kernels), as run_sampling.py would run them
+    (cudnn.benchmark=True, run_sampling.py:27): whole documents, TF32 off and on.  The >= 10x target's denominator."""
+    out = {}
+    try:
+        torch.backends.cudnn.benchmark = True
+        r = ReferenceRunner(a, device=str(dev))
+        if r.kind != "reference":
+            return {"unavailable": "reference tree (baseline/_ref) not present"}
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            r.doc(0); r.doc(1)
+            ts = [r.doc(2 + i)[2] for i in range(3)]
+            out[name + "_docs_per_s"] = 1.0 / (sum(ts) / len(ts))
+        out["what"] = "UNMODIFIED reference modules (baseline/_ref) on cuda: whole documents as written, wall clock with synchronize, 3 timed after 2 warm-up"
+    except Exception as e:                                       # noqa: BLE001
+        out["error"] = repr(e)[:300]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = True
+    return out
+
+
+def preprocessing_leg(dev):
+    """north_star: the segmentation / line preprocessing models stay the reference modules and are timed separately.
+    Random-init reference modules (val_TDiff.py:58-74) on a 288 x 288 input, CUDA events, ms per document."""
+    out = {}
+    try:
+        from oracle import ref_harness as RH
+        if not RH.available():
+            return {"unavailable": "reference tree (baseline/_ref) not present"}
+        nets = RH.build_preprocessing_nets()
+        x = torch.rand(1, 3, 288, 288, device=dev)
+        with torch.no_grad():
+            for name, m in nets.items():
+                m = m.to(dev)
+                try:
+                    for _ in range(3):
+                        m(x)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(5):
+                        m(x)
+                    e1.record(); e1.synchronize()
+                    out[name] = e0.elapsed_time(e1) / 5
+                except Exception as e:                           # noqa: BLE001
+                    out[name] = "error: " + repr(e)[:120]
+        out["what"] = ("reference modules, random-init, batch 1 @288x288, fp32 stock kernels; GeoTr_Seg_Inf = U2NETP + GeoTr whose GeoTr half is "
+                       "dead when use_init_flow=False (evaluation.py:176-180)")
+    except Exception as e:                                       # noqa: BLE001
+        out["error"] = repr(e)[:300]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(a):
     import torch.distributed as dist
     import synth_workload as synth                          # synthetic workload generator (no oracle code on this arm)
-    import dvd_b200
+    import dvd_b200                                          # noqa: F401
     from dvd_b200 import _lib
     from dvd_b200.model import DiT
     from dvd_b200.pipeline import DewarpPipeline
@@ -180,14 +273,18 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.lib()
+    _lib.lib()
+    scaling = "weak"
+    if a.total_docs:                                        # strong scaling: a fixed batch of documents split over the ranks
+        assert a.total_docs % world == 0, "--total-docs must be divisible by the number of GPUs"
+        a.docs = a.total_docs // world
+        scaling = "strong"
 
     # ---- synthetic workload: documents sharded by rank (doc id = step*world*docs + rank*docs + j); no collective on the path
     sd = synth.make_state_dict(1234, live_only=True)
     model = DiT(precision=a.precision)
     model.load_state_dict(sd, strict=False)
     model.to(dev)
-    pipe = DewarpPipeline(model, diffusion_steps=a.diffusion_steps, n_batch=a.n_batch, docs=a.docs, height=a.height, width=a.width)
     n_var = 2                                               # distinct input sets that the steps rotate through
     host_sets = []
     for v in range(n_var):
@@ -203,70 +300,67 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
-        barrier()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        pipe.kernel_launches = 0
-        t0 = time.perf_counter()
-        for i in range(steps):
-            flush.fill_(i & 0xFF)                                             # L2 flush between timed iterations (not timed)
-            evs[i][0].record()
-            fn(warmup + i)
-            evs[i][1].record()
-        barrier()
-        wall = time.perf_counter() - t0
-        launches = pipe.kernel_launches
-        ms = [s.elapsed_time(e) for s, e in evs]
-        return ms, wall, launches
+    def measure(precision, steps, warmup, with_e2e=True):
+        pipe = DewarpPipeline(model, diffusion_steps=a.diffusion_steps, n_batch=a.n_batch, docs=a.docs, height=a.height, width=a.width,
+                              precision=precision)
 
-    # (1) device-resident inputs
-    out_dev = [None]
+        def timed(fn):
+            for i in range(warmup):
+                fn(i)
+            barrier()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            pipe.kernel_launches = 0
+            for i in range(steps):
+                flush.fill_(i & 0xFF)                                         # L2 flush between timed iterations (not timed)
+                evs[i][0].record()
+                fn(warmup + i)
+                evs[i][1].record()
+            barrier()
+            return [s.elapsed_time(e) for s, e in evs], pipe.kernel_launches
 
-    def step_dev(i):
-        out_dev[0] = pipe.run_device(dev_sets[i % n_var])
+        def timed_e2e_pipelined():
+            """Throughput form of the same API (submit_host / wait, two batches outstanding): the uploads of batch i+1 and the download
+            of batch i overlap the kernels in between.  Every batch's H2D and D2H copies are inside the timed region."""
+            pending = None
+            for i in range(warmup):
+                t = pipe.submit_host(host_sets[i % n_var])
+                if pending is not None:
+                    pipe.wait(pending)
+                pending = t
+            pipe.wait(pending); pending = None
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                t = pipe.submit_host(host_sets[(warmup + i) % n_var])
+                if pending is not None:
+                    pipe.wait(pending)
+                pending = t
+            pipe.wait(pending)                                                # the last image is on the host
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1)
 
-    # (2) end to end through the public API: pinned host -> device -> ... -> host uint8 image
-    def step_e2e(i):
-        pipe.run_host(host_sets[i % n_var])
+        ms_dev, launches = timed(lambda i: pipe.run_device(dev_sets[i % n_var]))           # (1) device-resident inputs
+        res = {"pipe": pipe, "ms_dev": ms_dev, "launches": launches}
+        if with_e2e:
+            res["ms_e2e"], _ = timed(lambda i: pipe.run_host(host_sets[i % n_var]))        # (2) synchronous public-API calls: latency
+            res["ms_e2e_pipe"] = timed_e2e_pipelined()                                     # (3) two batches outstanding: throughput
+        return res
 
-    def timed_e2e_pipelined(steps, warmup):
-        """Throughput form of the same API (submit_host / wait, two batches outstanding): the uploads of batch i+1 and the download of
-        batch i overlap the kernels in between.  Every batch's H2D and D2H copies are inside the timed region; no L2 flush here (each
-        step streams 20+ MB of new inputs and > 126 MB of weights)."""
-        pending = None
-        for i in range(warmup):
-            t = pipe.submit_host(host_sets[i % n_var])
-            if pending is not None:
-                pipe.wait(pending)
-            pending = t
-        pipe.wait(pending); pending = None
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            t = pipe.submit_host(host_sets[(warmup + i) % n_var])
-            if pending is not None:
-                pipe.wait(pending)
-            pending = t
-        pipe.wait(pending)                                                    # the last image is on the host
-        e1.record()
-        barrier()
-        return e0.elapsed_time(e1)
+    def reduce_max(vals):
+        if world == 1:
+            return vals
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                              # max over ranks (timing only; not on the data path)
+        return [float(x) for x in t]
 
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.05)
-    ms_dev, wall_dev, launches = timed(step_dev, a.steps, a.warmup)
-    ms_e2e, wall_e2e, _ = timed(step_e2e, a.steps, a.warmup)              # synchronous calls: per-document latency
-    ms_e2e_pipe = timed_e2e_pipelined(a.steps, a.warmup)                     # two batches outstanding: throughput
+    main = measure(a.precision, a.steps, a.warmup)
     clocks = sampler.stop() if sampler else None
-
-    tot_dev, tot_e2e = sum(ms_dev) / 1e3, min(sum(ms_e2e), ms_e2e_pipe) / 1e3
-    if world > 1:
-        t = torch.tensor([tot_dev, tot_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)                              # max over ranks (timing only; not on the data path)
-        tot_dev, tot_e2e = float(t[0]), float(t[1])
+    pipe = main["pipe"]
+    tot_dev, tot_e2e = reduce_max([sum(main["ms_dev"]) / 1e3, min(sum(main["ms_e2e"]), main["ms_e2e_pipe"]) / 1e3])
     docs_total = a.docs * a.steps * world
     value, e2e = docs_total / tot_dev, docs_total / tot_e2e
 
@@ -274,31 +368,72 @@ def run_ours(a):
         peaks, which = measured_peaks()
         prof = pipe.profile_kernels(dev_sets[0])                             # CUDA-event timing of the dominant kernels, L2-flushed
         gflop = algorithmic_gflop_per_doc(a.diffusion_steps, a.n_batch) * a.docs
+        dtype = {"bf16x3": "bf16x3 (split-bf16 operands, 3 tcgen05 passes, fp32 accumulate: fp32-accurate)", "bf16": "bf16", "fp32": "f32"}[a.precision]
         line = {"metric": "dewarped docs/sec (sampling+unwarp)", "value": value, "unit": "docs/s", "n_gpus": world, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": tot_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
-                "config": {"workload": workload_name(a), "docs_per_step_per_gpu": a.docs, "photo_hw": [a.height, a.width],
-                           "diffusion_steps": a.diffusion_steps, "n_batch": a.n_batch, "weights": "random-init (synth_workload.py seed 1234)",
-                           "l2": "256 MiB flush write between timed iterations (value, synchronous e2e); pipelined e2e: no flush, every step streams new inputs and > 126 MB of weights", "cuda_graph": pipe.use_graph, "parallelism": f"document-sharded x{world}, no collective"},
-                "p50_latency_ms": statistics.median(ms_dev),
+                "warmup": a.warmup, "ms_per_step": tot_dev / a.steps * 1e3, "higher_is_better": True, "scaling": scaling,
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config_dict(a),
+                "run": {"cuda_graph": pipe.use_graph, "parallelism": f"document-sharded x{world}, no collective", "precision": a.precision},
+                "p50_latency_ms": statistics.median(main["ms_dev"]),
                 "e2e": {"value": e2e, "unit": "docs/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-                        "p50_latency_ms": statistics.median(ms_e2e), "io": "uint8 HWC photo in, uint8 HWC dewarped image out",
+                        "p50_latency_ms": statistics.median(main["ms_e2e"]), "io": "uint8 HWC photo in, uint8 HWC dewarped image out",
                         "mode": "submit_host/wait, two batches outstanding (uploads and downloads overlap the kernels of the batch in between)",
-                        "synchronous_docs_per_s": a.docs * a.steps * world / (sum(ms_e2e) / 1e3)},      # rank 0's clock x world
-                "gpu_launches": int(launches),
+                        "synchronous_docs_per_s": a.docs * a.steps * world / (sum(main["ms_e2e"]) / 1e3)},      # rank 0's clock x world
+                "gpu_launches": int(main["launches"]),
                 "clocks": clocks,
                 "denoiser_tflops_effective": gflop / 1e3 / (tot_dev / a.steps / 1.0) if tot_dev > 0 else None,
                 "roofline": prof["roofline"], "roofline_unwarp": prof["roofline_unwarp"], "kernel_share": prof.get("share"),
                 "peaks": which}
-        if not a.no_cpu_baseline:
+        extras = world == 1 and not a.no_extras
+        if extras:
+            # ---- the other two precision modes on the same workload (device-resident value + pipelined e2e)
+            try:
+                for prec, key, st in (("bf16", "bf16_mode", a.steps), ("fp32", "fp32_mode", min(a.steps, 3))):
+                    if prec == a.precision:
+                        continue
+                    r = measure(prec, st, 3, with_e2e=(prec == "bf16"))
+                    o = {"value": a.docs * st / (sum(r["ms_dev"]) / 1e3), "unit": "docs/s", "ms_per_step": sum(r["ms_dev"]) / st,
+                         "gpu_launches": int(r["launches"])}
+                    if prec == "bf16":
+                        o["e2e"] = a.docs * st / (min(sum(r["ms_e2e"]), r["ms_e2e_pipe"]) / 1e3)
+                        pr = r["pipe"].profile_kernels(dev_sets[0], iters=4, with_unwarp=False)
+                        o["roofline_frac"] = pr["roofline"]["frac"]; o["gemm_tflops"] = pr["roofline"]["achieved"]
+                        o["attention_tflops"] = pr["roofline"]["attention_tflops"]
+                        o["accuracy"] = "single pass: map error ~6e-4 normalised (0.6 px at 2000 px), image PSNR below the 45 dB gate - reduced-accuracy mode"
+                    else:
+                        o["accuracy"] = "FFMA reference mode (no tensor cores), bit-reproducible"
+                    line[key] = o
+                    del r
+            except Exception as e:                                           # noqa: BLE001
+                line["bf16_mode_error"] = repr(e)[:300]
+        if world == 1 and not a.no_cpu_baseline:
+            # ---- one document through the reference on the host cores: the cpu_baseline AND the parity check of the timed precision
             torch.set_num_threads(os.cpu_count())
-            sd_full = synth.make_state_dict(1234)
-            inp = synth.make_doc_inputs(0, H=a.height, W=a.width)
-            photo = inp.pop("photo")
-            sec, t_den, t_unw = cpu_reference_doc_seconds(a, sd_full, inp, photo, full=False)
-            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "docs/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"1 document: 1 of {a.diffusion_steps} as-written denoiser forwards x{a.diffusion_steps} "
-                                              f"({t_den:.1f} s) + full-size unwarp ({t_unw:.2f} s)"}
+            r = ReferenceRunner(a)
+            ref_img, ref_map, sec = r.doc(0)
+            line["cpu_baseline"] = {"value": a.docs / sec / a.docs, "unit": "docs/s", "cores": torch.get_num_threads(), "kind": r.kind,
+                                    "sample": f"1 whole document through the reference as written ({sec:.1f} s: S x n_batch forwards with all 12 DiT "
+                                              "blocks, debug PNG dumps, full-size unwarp + uint8 cast)"}
+            try:
+                d0 = synth.make_doc_inputs(0, H=a.height, W=a.width)
+                one = DewarpPipeline(model, diffusion_steps=a.diffusion_steps, n_batch=a.n_batch, docs=1, height=a.height, width=a.width,
+                                     precision=a.precision)
+                dset = {k: d0[k].to(dev).contiguous() for k in ("y512", "mask_cat", "mask_y512", "line_msk", "x_T")}
+                dset["photo_u8"] = d0["photo"].permute(0, 2, 3, 1).to(torch.uint8).contiguous().to(dev)
+                img = one.run_device(dset).cpu()
+                err = (one.map64.cpu() - ref_map).abs()
+                line["parity"] = {"vs": f"{r.kind} on this box's CPU, document 0, same weights and seeded noise", "precision": a.precision,
+                                  "map_err_mean_px_at_4032": float(err.mean()) * 2015.5, "map_err_max_px_at_4032": float(err.max()) * 2015.5,
+                                  "map_err_mean_norm": float(err.mean()), "map_err_max_norm": float(err.max()),
+                                  "image_psnr_db_uint8": psnr_db(img[0].float(), torch.from_numpy(ref_img).float()),
+                                  "gates": "map <= 0.05 px mean / 0.5 px max; image PSNR >= 45 dB"}
+            except Exception as e:                                           # noqa: BLE001
+                line["parity_error"] = repr(e)[:300]
+        if extras:
+            line["torch_b200"] = torch_b200_leg(a, dev)
+            if "fp32_docs_per_s" in line["torch_b200"]:
+                line["torch_b200"]["speedup_vs_fp32"] = value / line["torch_b200"]["fp32_docs_per_s"]
+                line["torch_b200"]["speedup_vs_tf32"] = value / line["torch_b200"]["tf32_docs_per_s"]
+            line["preprocessing_ms"] = preprocessing_leg(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdvd_b200.so")
+LIB_PATH = os.environ.get("DVD_LIB", os.path.join(_HERE, "libdvd_b200.so"))      # DVD_LIB: instrumented build (tools/gemm_trace.py)
 
 PREC_FP32 = 0
 PREC_BF16 = 1
@@ -56,7 +56,6 @@ SIGNATURES = {
     "dvd_grid_sample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dvd_fullres_grid_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "dvd_workspace_bytes": (_sz, [_i, _i, _i]),
-    "dvd_workspace_init": (_i, [_vp, _sz, _i, _i, _i, _vp]),
     "dvd_tables_init": (_i, [_WP, _FP, _i, _vp, _vp]),
     "dvd_static_forward": (_i, [_WP, _vp, _sz, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "dvd_denoise_step": (_i, [_WP, _vp, _sz, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _f, _f, _vp, _vp, _vp]),
@@ -66,7 +65,7 @@ SIGNATURES = {
     "dvd_workspace_tensor": (_vp, [_vp, _i, _i, _i, C.c_char_p, C.POINTER(C.c_longlong)]),
     "dvd_test_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "dvd_test_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
-    "dvd_gemm_bf16": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "dvd_gemm_bf16": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "dvd_debug_stop_after": (_i, [_i]),
     "dvd_profile_begin": (_i, []),
     "dvd_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -21,7 +21,11 @@ LIB = os.path.join(HERE, "libdvd_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-FLAGS += os.environ.get("DVD_NVCC_EXTRA", "").split()       # e.g. -DDVD_GEMM_TRACE for tools/gemm_trace.py (instrumented build)
+EXTRA = os.environ.get("DVD_NVCC_EXTRA", "").split()        # e.g. -DDVD_GEMM_TRACE for tools/gemm_trace.py (instrumented build)
+if EXTRA:                                                   # instrumented builds never replace the product library
+    FLAGS += EXTRA
+    BUILD = os.path.join(CSRC, "build_trace")
+    LIB = os.path.join(HERE, "libdvd_b200_trace.so")
 SOURCES = ["api.cu", "unwarp.cu", "gemm_simt.cu", "misc.cu", "gemm_tc.cu", "gemm_pair.cu", "attn_tc.cu", "denoiser.cu"]
 
 

@@ -63,7 +63,7 @@ extern "C" int dvd_check_device(void) {
 }
 
 // A[M,K] fp32, W[N,K] fp32 -> C[M,N] = A W^T + bias.  In the tensor modes the operands are first converted into `scratch`
-// (bf16: (M+N)*K*2 bytes; bf16x3: twice that, plus 48 KB of split-K state when `splitk` != 0) and the tcgen05 kernels are used.
+// (bf16: (M+N)*K*2 bytes; bf16x3: twice that) and the tcgen05 kernels are used.
 extern "C" int dvd_test_gemm(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int precision,
                              void* scratch, size_t scratch_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -77,9 +77,7 @@ extern "C" int dvd_test_gemm(const float* A, const float* W, const float* bias, 
   const bool x3 = precision == DVD_PREC_BF16X3;
   auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
   const size_t a_b = al((size_t)M * K * 2), w_b = al((size_t)N * K * 2);
-  // optional split-K state behind the operands: 3 fp32 slices + 4096 counters (zeroed here, outside any timed region)
   const size_t ops = (x3 ? 2 : 1) * (a_b + w_b);
-  const size_t sk_b = al((size_t)3 * M * N * 4) + 4096 * 4;
   DVD_REQUIRE(scratch && scratch_bytes >= ops, "test_gemm: scratch needs %zu bytes", ops);
   char* base = (char*)scratch;
   TcMat a, w;
@@ -93,13 +91,7 @@ extern "C" int dvd_test_gemm(const float* A, const float* W, const float* bias, 
     rc = f32_to_bf16(A, (__nv_bfloat16*)a.hi, (long long)M * K, st); if (rc) return rc;
     rc = f32_to_bf16(W, (__nv_bfloat16*)w.hi, (long long)N * K, st); if (rc) return rc;
   }
-  TcScratch sk;
-  if (scratch_bytes >= ops + sk_b) {
-    sk.partial = (float*)(base + ops); sk.partial_floats = (size_t)3 * M * N;
-    sk.counters = (unsigned int*)(base + ops + al((size_t)3 * M * N * 4)); sk.n_counters = 4096;
-    DVD_CUDA(cudaMemsetAsync(sk.counters, 0, 4096 * 4, st));
-  }
-  return gemm_tc(a, w, M, N, K, e, sk.partial ? &sk : nullptr, st);
+  return gemm_tc(a, w, M, N, K, e, st);
 }
 
 // q,k,v,o: [batch, T, heads*d] fp32.  fp32 mode: scratch holds the [batch*heads, T, T] scores.
@@ -148,18 +140,12 @@ extern "C" int dvd_test_attention(const float* q, const float* k, const float* v
 }
 
 // Plain tensor-core GEMM entry point (tuning / micro-benchmarks): out = A W^T + bias, bf16 output (and optional fp32 output).
-// A16_lo / W16_lo non-null: split-precision pairs (three passes).  splitk_scratch (optional): >= 3*M*N*4 + 16 KB, zero-initialised.
+// A16_lo / W16_lo non-null: split-precision pairs (three passes).
 extern "C" int dvd_gemm_bf16(const void* A16, const void* A16_lo, int lda, const void* W16, const void* W16_lo, int ldw, const float* bias,
-                             void* out16, float* out32, int M, int N, int K, void* splitk_scratch, size_t splitk_bytes, void* stream) {
+                             void* out16, float* out32, int M, int N, int K, void* stream) {
   Epilogue e; e.bias = bias; e.out_bf16 = (__nv_bfloat16*)out16; e.ldc_bf16 = N; e.out = out32; e.ldc = N;
   TcMat a, w;
   a.hi = (const __nv_bfloat16*)A16; a.lo = (const __nv_bfloat16*)A16_lo; a.ld = lda;
   w.hi = (const __nv_bfloat16*)W16; w.lo = (const __nv_bfloat16*)W16_lo; w.ld = ldw;
-  TcScratch sk;
-  const size_t need = (size_t)3 * M * N * 4 + 4096 * 4;
-  if (splitk_scratch && splitk_bytes >= need) {
-    sk.partial = (float*)splitk_scratch; sk.partial_floats = (size_t)3 * M * N;
-    sk.counters = (unsigned int*)((char*)splitk_scratch + (size_t)3 * M * N * 4); sk.n_counters = 4096;
-  }
-  return gemm_tc(a, w, M, N, K, e, sk.partial ? &sk : nullptr, (cudaStream_t)stream);
+  return gemm_tc(a, w, M, N, K, e, (cudaStream_t)stream);
 }

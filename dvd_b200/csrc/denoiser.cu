@@ -18,9 +18,6 @@ namespace dvd {
 
 struct B16 { __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; };
 
-constexpr size_t kSplitKFloats = (size_t)12 << 20;      // 48 MB of fp32 split-K slices
-constexpr int kSplitKCounters = 4096;
-
 struct Workspace {
   // static, per document
   float *y4, *pyrP, *pyrQ, *feat, *a_stat, *ctx[3], *kv_static[3];
@@ -33,8 +30,6 @@ struct Workspace {
   // attention operands: bf16 (DVD_PREC_BF16) or fp16 (DVD_PREC_BF16X3)
   __nv_bfloat16 *q16, *kv_static16[3], *kv_r16, *qkv16, *qkv_d16;       // Q, K row-major
   __nv_bfloat16 *vt_static16[3], *vt_r16, *vt_qkv16, *vt_d16;            // V^T [sample, C_v, 1024] written by the GEMM epilogues
-  TcScratch sk;                            // split-K slices + tile counters of the persistent GEMM
-  size_t counters_off;                     // byte offset of the counters (zeroed by dvd_workspace_init)
   size_t s_floats;
   size_t step_off;                         // offset of the per-step region
   size_t total_bytes;
@@ -66,9 +61,6 @@ static void carve_static(Carver& k, Workspace& w, int docs, int n_hyp, bool tc, 
     for (int i = 0; i < 3; ++i) w.ctx16[i] = k.P(Md * 384, x3);
     for (int i = 0; i < 3; ++i) w.kv_static16[i] = k.H(Md * 768);
     for (int i = 0; i < 3; ++i) w.vt_static16[i] = k.H(Md * 384);
-    w.sk.partial = k.F(kSplitKFloats); w.sk.partial_floats = kSplitKFloats;
-    w.counters_off = k.off;
-    w.sk.counters = (unsigned int*)k.take(kSplitKCounters * sizeof(unsigned int)); w.sk.n_counters = kSplitKCounters;
   }
 }
 
@@ -191,7 +183,7 @@ static int linear(const Ctx& c, const float* A32, const B16& A16, int lda, const
     a.hi = A16.hi; a.lo = c.x3() ? A16.lo : nullptr; a.ld = lda;
     w.hi = (const __nv_bfloat16*)W.bf16 + (size_t)row0 * W.k; w.ld = W.k;
     w.lo = c.x3() ? (const __nv_bfloat16*)W.bf16_lo + (size_t)row0 * W.k : nullptr;
-    return gemm_tc(a, w, M, N, W.k, e, &c.ws.sk, c.st);
+    return gemm_tc(a, w, M, N, W.k, e, c.st);
   }
   GemmParams p = linear_params(A32, lda, W.f32 + (size_t)row0 * W.k, M, N, W.k);
   p.e = e;
@@ -238,7 +230,7 @@ static int static_forward(const Ctx& c, const float* y512, const float* mask_cat
       DVD_TRY(im2col3x3_c4_bf16(s.y4, Q.hi, Q.lo, B, 512, 512, st));                  // Q: [B*512*512, 64]
       Epilogue e; e.bias = w.pyr_b[0]; e.act = ACT_RELU; out_operand(e, P, 64);
       TcMat wt = weight_op(c, w.pyr[0]); wt.ld = 64;
-      DVD_TRY(gemm_tc(op(Q), wt, B * 512 * 512, 64, 64, e, nullptr, st));
+      DVD_TRY(gemm_tc(op(Q), wt, B * 512 * 512, 64, 64, e, st));
     }
     auto conv = [&](const B16& in, const B16& out, int H, int Cin, int layer) -> int {
       const int Cout = w.pyr[layer].n;
@@ -439,15 +431,6 @@ using namespace dvd;
 extern "C" size_t dvd_workspace_bytes(int docs, int n_hyp, int precision) {
   if (docs <= 0 || n_hyp <= 0) return 0;
   return carve(nullptr, docs, n_hyp, precision).total_bytes;
-}
-
-extern "C" int dvd_workspace_init(void* workspace, size_t workspace_bytes, int docs, int n_hyp, int precision, void* stream) {
-  DVD_REQUIRE(workspace && docs > 0 && n_hyp > 0, "workspace_init: bad args");
-  DVD_REQUIRE(precision == DVD_PREC_FP32 || precision == DVD_PREC_BF16 || precision == DVD_PREC_BF16X3, "bad precision %d", precision);
-  Workspace w = carve(workspace, docs, n_hyp, precision);
-  if (w.total_bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", w.total_bytes, workspace_bytes); return DVD_E_WORKSPACE; }
-  if (w.sk.counters) DVD_CUDA(cudaMemsetAsync(w.sk.counters, 0, (size_t)w.sk.n_counters * sizeof(unsigned int), (cudaStream_t)stream));
-  return 0;
 }
 
 extern "C" const float* dvd_workspace_feat(void* workspace, int docs, int n_hyp, int precision) {

@@ -357,12 +357,13 @@ static int launch_tc_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmAl,
   return launch_tc<128, CONV, X3>(tmA, tmAl, tmB, tmBl, M, N, K, e, cg, st);
 }
 
-int gemm_tc(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, const TcScratch* sk, cudaStream_t st) {
+int gemm_tc(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, cudaStream_t st) {
   DVD_REQUIRE(A.hi && W.hi && (e.out || e.out_bf16), "gemm_tc: null pointer");
   DVD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && M % 128 == 0, "gemm_tc: bad shape M=%d N=%d K=%d (M must be a multiple of 128)", M, N, K);
   DVD_REQUIRE((A.lo != nullptr) == (W.lo != nullptr), "gemm_tc: A and W must both be split pairs or both plain");
   int rc = check_epilogue(e, N); if (rc) return rc;
-  if (!use_v1() && gemm_pair_supported(M, N, K, false)) return gemm_pair_dispatch(A, W, M, N, K, e, 0, 0, 0, 0, sk, st);
+  const bool periods_ok = e.resid_mod % 128 == 0 && e.pos_rows % 128 == 0 && e.group_rows % 128 == 0;
+  if (!use_v1() && periods_ok && gemm_pair_supported(M, N, K, false)) return gemm_pair_dispatch(A, W, M, N, K, e, 0, 0, 0, 0, st);
   const bool x3 = A.lo != nullptr;
   // wide tiles only when they still fill the machine
   const bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) * 100 >= 190LL * sm_count());
@@ -390,7 +391,7 @@ int conv3x3_tc(const TcMat& in, const TcMat& Wt, int B, int H, int Wd, int Cin, 
   int rc = check_epilogue(e, Cout); if (rc) return rc;
   if (!use_v1() && gemm_pair_supported(M, Cout, K, true)) {
     TcMat w = Wt; w.ld = K;
-    return gemm_pair_dispatch(in, w, M, Cout, K, e, B, H, Wd, Cin, nullptr, st);
+    return gemm_pair_dispatch(in, w, M, Cout, K, e, B, H, Wd, Cin, st);
   }
   const bool x3 = in.lo != nullptr;
   const int bn = Cout == 64 ? 64 : ((Cout % 256 == 0 && (long long)(M / 128) * (Cout / 256) >= 2LL * sm_count()) ? 256 : 128);

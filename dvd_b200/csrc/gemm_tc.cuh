@@ -15,22 +15,13 @@ struct TcMat {
   int ld = 0;
 };
 
-// Split-K workspace of the persistent kernel (optional): (splits-1) fp32 partial tiles per output element and one arrival counter
-// per output tile.  The counters must be ZERO before the first launch and are left zero by every launch.
-struct TcScratch {
-  float* partial = nullptr;
-  size_t partial_floats = 0;
-  unsigned int* counters = nullptr;
-  int n_counters = 0;
-};
-
 // C[M,N] = epilogue(A[M,K] * W[N,K]^T), fp32 accumulate in TMEM.  M % 128 == 0, K % 8 == 0, N % 4 == 0.
-int gemm_tc(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, const TcScratch* sk, cudaStream_t st);
+int gemm_tc(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, cudaStream_t st);
 inline int gemm_tc_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, const Epilogue& e,
                         cudaStream_t st) {
   TcMat a; a.hi = A; a.ld = lda;
   TcMat w; w.hi = W; w.ld = ldw;
-  return gemm_tc(a, w, M, N, K, e, nullptr, st);
+  return gemm_tc(a, w, M, N, K, e, st);
 }
 
 // 3x3 / pad 1 conv as implicit GEMM on tcgen05 (TMA boxes over the NHWC activation, zero padding by OOB fill):
@@ -57,6 +48,6 @@ int sm_count();       // SMs of the current device (cached per device)
 // ---- internal: persistent CTA-pair kernel (gemm_pair.cu); conv_h > 0 selects the implicit-GEMM mode
 bool gemm_pair_supported(int M, int N, int K, bool conv);
 int gemm_pair_dispatch(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, int conv_b, int conv_h, int conv_w,
-                       int conv_cin, const TcScratch* sk, cudaStream_t st);
+                       int conv_cin, cudaStream_t st);
 
 }  // namespace dvd

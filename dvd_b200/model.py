@@ -53,7 +53,6 @@ class Engine:
         off = (-self.ws.data_ptr()) % 256
         self.ws_ptr = C.c_void_p(self.ws.data_ptr() + off)
         self.N = docs * n_hyp
-        _lib.check(self.lib.dvd_workspace_init(self.ws_ptr, self.ws_bytes, docs, n_hyp, self.prec, _lib.stream_ptr()), "dvd_workspace_init")
 
     def tables(self, t_values) -> torch.Tensor:
         """dvd_tables_init for a list of (already remapped) timesteps -> [len, TABLE_ROW] device tensor.  Cached on the packed

@@ -170,7 +170,7 @@ class DewarpPipeline:
         return self.wait(self.submit_host(h))
 
     # ---- measurement helpers used by bench.py
-    def profile_kernels(self, d: dict, iters: int = 5) -> dict:
+    def profile_kernels(self, d: dict, iters: int = 5, with_unwarp: bool = True) -> dict:
         """CUDA-event timing (on the launch stream, L2 flushed between runs) of the kernel classes inside a real step, and of
         the unwarp kernel; returns the roofline objects of the bench JSON line."""
         peaks_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -212,6 +212,8 @@ class DewarpPipeline:
                     # k-step to be fp32-accurate, so its tensor pipe does `mma_passes` x that work: frac_executed is the pipe's own load.
                     "mma_passes": passes, "executed_tflops": gemm_tf * passes, "frac_executed": gemm_tf * passes / peak_tf,
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % which) if tensor_mode else "nominal fp32 FFMA"}
+            if not with_unwarp:
+                return {"roofline": roof, "share": share}
             # unwarp: fp32 contract (24 B/px) and the uint8 variant actually used end to end (6 B/px).  20 launches replayed from one
             # CUDA graph (no host time between launches) over rotating buffer pairs whose total exceeds the L2, so every launch
             # reads its photo from HBM.

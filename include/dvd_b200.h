@@ -124,9 +124,6 @@ DVD_API int dvd_fullres_grid_f32(const float* map, float* grid, int B, int H, in
 
 /* ---- denoiser + sampler ------------------------------------------------------------------- */
 DVD_API size_t dvd_workspace_bytes(int docs, int n_hyp, int precision);
-/* Once after allocating a workspace (and before its first use): zeroes the split-K tile counters of the persistent GEMM,
- * which every later launch leaves at zero again. */
-DVD_API int dvd_workspace_init(void* workspace, size_t workspace_bytes, int docs, int n_hyp, int precision, void* stream);
 
 /* CM:97-139 + CM:209-211 + CM:331: conditioning tables for `n_steps` scalar timesteps
  * (values AFTER the CM:575-579 remap).  tables [n_steps][DVD_TABLE_ROW]. */
@@ -187,10 +184,9 @@ DVD_API int dvd_test_attention(const float* q, const float* k, const float* v, f
                        int T, int d, float scale, int precision, void* scratch, size_t scratch_bytes,
                        void* stream);
 /* Plain tensor-core GEMM (tuning / micro-benchmarks): out = A[M,K] W[N,K]^T + bias; bf16 operands (A16_lo / W16_lo non-NULL:
- * split pairs, three passes), bf16 and/or fp32 output.  splitk_scratch: optional zero-initialised 3*M*N*4 + 16 KB bytes. */
+ * split pairs, three passes), bf16 and/or fp32 output. */
 DVD_API int dvd_gemm_bf16(const void* A16, const void* A16_lo, int lda, const void* W16, const void* W16_lo, int ldw,
-                          const float* bias, void* out16, float* out32, int M, int N, int K, void* splitk_scratch,
-                          size_t splitk_bytes, void* stream);
+                          const float* bias, void* out16, float* out32, int M, int N, int K, void* stream);
 /* Kernel-class profiler: between begin/end every dense contraction launched by this thread is bracketed by CUDA
  * events.  end() synchronises and returns, for the classes {0: GEMM, 1: attention, 2: pyramid conv}, the summed
  * device time (ms), algorithmic FLOPs and launch counts. */

@@ -1,9 +1,9 @@
-"""Runs the UNMODIFIED reference (/root/reference) for the hot path (TEST INFRASTRUCTURE).
+"""Runs the UNMODIFIED reference for the hot path (TEST / BASELINE INFRASTRUCTURE, never the product path).
 
-Only usable in the build container: /root/reference does not exist on the GPU box, so nothing in
-``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports this module.  It is used by
-``oracle/make_golden.py`` to generate ``tests/golden/*.npz`` and by the optional
-``tests/test_oracle_vs_reference.py`` (skipped when /root/reference is absent).
+Where the reference comes from: ``/root/reference`` in the build container; on the GPU box that tree does not exist, so
+``__graft_entry__.build()`` copies it verbatim (Python sources only, no edits) to the git-ignored ``baseline/_ref/`` which
+travels with the gpurun snapshot.  Users: ``oracle/make_golden.py`` (golden fixtures), ``tests/test_reference_dropin.py``
+and the baseline legs of ``bench.py`` (``--impl reference``, ``cpu_baseline``, ``torch_b200``, ``preprocessing``).
 
 Import shims (``oracle/ref_shims``) restate the few third-party classes the reference imports but
 this image lacks (timm, mmcv, mmengine, mpi4py, blobfile, matplotlib, h5py); the reference code
@@ -18,8 +18,31 @@ import tempfile
 
 import torch
 
-REF_ROOT = os.environ.get("DVD_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "ref_shims")
+BASELINE_REF = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+
+
+def _find_root() -> str:
+    for cand in (os.environ.get("DVD_REFERENCE_ROOT"), BASELINE_REF, "/root/reference"):
+        if cand and os.path.isdir(os.path.join(cand, "train_settings", "dvd")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
+
+
+def install_baseline_ref(src: str = "/root/reference") -> bool:
+    """Verbatim copy of the reference's Python sources to baseline/_ref (git-ignored, ships with gpurun).  The reference has no
+    setup.py / pyproject, so there is nothing to pip-install: it is imported from this directory through sys.path."""
+    import shutil
+    if not os.path.isdir(os.path.join(src, "train_settings", "dvd")):
+        return False
+    if os.path.isdir(BASELINE_REF):
+        shutil.rmtree(BASELINE_REF)
+    shutil.copytree(src, BASELINE_REF, ignore=shutil.ignore_patterns(".git", "asset", "matlab_code", "__pycache__", "*.pyc", "*.png", "*.jpg"))
+    return True
 
 
 def available() -> bool:
@@ -112,3 +135,22 @@ def reference_unwarp(map64: torch.Tensor, photo: torch.Tensor):
     sample = (((sample + base.to(sample.device)) * 1) * 2 - 1) * 0.987
     reg = register_model2((512, 512), "bilinear")
     return sample, reg([photo.float(), sample])
+
+
+# ----------------------------------------------------------------------------------------------- baseline timing legs (bench.py)
+def reference_document(model, inp: dict, photo: torch.Tensor, S: int, n_batch: int, seed: int, device: str = "cpu"):
+    """One whole document through the reference's own code: evaluation.py:80-138 (sampling, incl. its three debug PNG dumps) +
+    :300-306 (upsample / affine) + visualization_utils.py:75-77 (grid_sample, uint8 cast).  Returns the HWC uint8 image."""
+    dev = torch.device(device)
+    inp_d = {k: v.to(dev) for k, v in inp.items()}
+    sample, _ = reference_sample(model, inp_d, S=S, n_batch=n_batch, seed=seed)
+    _, img = reference_unwarp(sample, photo.to(dev))
+    return img[0].permute(1, 2, 0).cpu().numpy().astype("uint8")
+
+
+def build_preprocessing_nets():
+    """The three preprocessing networks of val_TDiff.py:58-74, random-init (the checkpoints are not in the tree)."""
+    _setup_path()
+    from train_settings.models.geotr.geotr_core import GeoTr_Seg_Inf, Seg
+    from train_settings.models.geotr.unet_model import UNet
+    return {"GeoTr_Seg_Inf": GeoTr_Seg_Inf().eval(), "Seg(U2NETP)": Seg().eval(), "line UNet": UNet(n_channels=3, n_classes=1).eval()}

@@ -234,7 +234,7 @@ def _run_gemm(dev, M, N, K, prec):
     A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
     Ad, Wd, bd = A.to(dev), W.to(dev), b.to(dev)
     Cd = torch.empty(M, N, device=dev)
-    scratch = torch.zeros((M + N) * K * 4 + 3 * M * N * 4 + (64 << 10), dtype=torch.uint8, device=dev)   # operands (+ lo) + split-K state
+    scratch = torch.empty((M + N) * K * 4 + (64 << 10), dtype=torch.uint8, device=dev)   # 16-bit operands (+ lo halves)
     _lib.check(_lib.lib().dvd_test_gemm(_lib.ptr(Ad), _lib.ptr(Wd), _lib.ptr(bd), _lib.ptr(Cd), M, N, K, prec, _lib.ptr(scratch),
                                         scratch.numel(), _lib.stream_ptr()), "dvd_test_gemm")
     torch.cuda.synchronize()
@@ -259,8 +259,8 @@ def test_gemm_bf16_tcgen05(dev, M, N, K):
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 1032), (2048, 1536, 1536), (8192, 1152, 384), (2048, 4608, 1536),
                                    (8192, 384, 1536), (2048, 1536, 2048), (2048, 2048, 1536), (512, 64, 64), (384, 192, 128)])
 def test_gemm_bf16x3_tcgen05(dev, M, N, K):
-    """Split-precision GEMM (three tcgen05 passes): fp32-accurate.  Covers the persistent CTA-pair kernel with and without split-K
-    (the M = 2048 decoder shapes), every tile width, and the generic single-CTA kernel (M = 128 / 384)."""
+    """Split-precision GEMM (three tcgen05 passes): fp32-accurate.  Covers the persistent CTA-pair kernel on the decoder / DiT shapes,
+    every tile width, and the generic single-CTA kernel (M = 128 / 384)."""
     Cg, A, W, b = _run_gemm(dev, M, N, K, 2)
     ref = (A.double() @ W.double().t() + b.double()).float()
     err = float((Cg - ref).abs().max()) / max(1.0, float(ref.abs().max()))
@@ -277,7 +277,7 @@ def test_gemm_bf16_more_row_tiles_than_grid_y(dev):
     W = (torch.randn(N, K, device=dev, generator=g) / K ** 0.5).bfloat16()
     b = torch.randn(N, device=dev, generator=g)
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    _lib.check(_lib.lib().dvd_gemm_bf16(_lib.ptr(A), None, K, _lib.ptr(W), None, K, _lib.ptr(b), _lib.ptr(out), None, M, N, K, None, 0,
+    _lib.check(_lib.lib().dvd_gemm_bf16(_lib.ptr(A), None, K, _lib.ptr(W), None, K, _lib.ptr(b), _lib.ptr(out), None, M, N, K,
                                         _lib.stream_ptr()), "gemm")
     torch.cuda.synchronize()
     for r0 in (0, 32768 * 128 - 64, 65535 * 128 - 64, 65536 * 128 - 64, M - 256):      # start, z-slice boundaries, ragged tail
@@ -535,10 +535,10 @@ def test_bf16_mode_image_error_is_reported_not_gated(dev, models, golden_dir, ca
 
 
 # ----------------------------------------------------------------------------------------------- kernel variants and the evaluation drop-in
-@pytest.mark.parametrize("env", [{"DVD_GEMM_V1": "1"}, {}, {"DVD_GEMM_SPLITS": "2"}, {"DVD_GEMM_SPLITS": "4"}, {"DVD_GEMM_BN": "128"},
-                                 {"DVD_GEMM_BN": "192"}, {"DVD_GEMM_BN": "64", "DVD_GEMM_SPLITS": "3"}])
+@pytest.mark.parametrize("env", [{"DVD_GEMM_V1": "1"}, {}, {"DVD_GEMM_BN": "256"}, {"DVD_GEMM_BN": "192"}, {"DVD_GEMM_BN": "128"},
+                                 {"DVD_GEMM_BN": "64"}])
 def test_gemm_kernel_variants_agree(dev, env):
-    """The tcgen05 GEMM kernels (generic single-CTA; persistent CTA-pair with every tile width and split-K factor) are selected by
+    """The tcgen05 GEMM kernels (generic single-CTA; persistent CTA-pair with every tile width) are selected by
     shape at run time; force each configuration (env is read once per process, hence the subprocess) over the denoiser's shapes in
     both tensor modes."""
     import subprocess, sys

@@ -1,6 +1,10 @@
-"""Micro-benchmark of the tcgen05 GEMM on the denoiser's shapes (CUDA events, L2 flushed between runs), both tensor modes.
-Usage: python tools/gemm_bench.py [--check]      env: DVD_GEMM_V1=1 selects the generic single-CTA kernel; DVD_GEMM_BN / DVD_GEMM_SPLITS
-force the tile width / split-K factor of the persistent CTA-pair kernel.  --check: fewer timing runs (used by the parity tests)."""
+"""Micro-benchmark of the tcgen05 GEMM on the denoiser's shapes, both tensor modes.
+Usage: python tools/gemm_bench.py [--check] [--graph]
+  default : one launch per measurement between CUDA events, L2 flushed in between (includes the launch gap of an eager launch)
+  --graph : 16 launches captured in ONE CUDA graph over rotating weight / output buffers (> L2 in total), replayed: the time per
+            launch a step of the pipeline sees (no host time between kernels)
+  --check : fewer runs (used by the parity tests)
+env: DVD_GEMM_V1=1 selects the generic single-CTA kernel; DVD_GEMM_BN forces the tile width of the persistent CTA-pair kernel; DVD_GEMM_DEBUG=1 prints the chosen configuration per launch."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,30 +16,50 @@ SHAPES = [(2048, 4608, 1536, "dec qkv"), (2048, 1536, 1536, "dec fc"), (2048, 20
 
 
 def main():
-    check = "--check" in sys.argv
+    check, graph = "--check" in sys.argv, "--graph" in sys.argv
     lib = _lib.lib()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    tag = f"v1={os.environ.get('DVD_GEMM_V1','0')} bn={os.environ.get('DVD_GEMM_BN','auto')} sp={os.environ.get('DVD_GEMM_SPLITS','auto')}"
-    for mode in ("bf16", "bf16x3"):
+    tag = f"v1={os.environ.get('DVD_GEMM_V1','0')} bn={os.environ.get('DVD_GEMM_BN','auto')}"
+    modes = [m for m in ("bf16", "bf16x3") if ("--" + m) in sys.argv] or ["bf16", "bf16x3"]
+    for mode in modes:
         for M, N, K, name in SHAPES:
             A = torch.randn(M, K, device=dev) * 0.5; W = torch.randn(N, K, device=dev) / K ** 0.5
             Ah, Wh = A.bfloat16(), W.bfloat16()
             Al = (A - Ah.float()).bfloat16() if mode == "bf16x3" else None
             Wl = (W - Wh.float()).bfloat16() if mode == "bf16x3" else None
             b = torch.randn(N, device=dev); out = torch.empty(M, N, device=dev)
-            sk = torch.zeros(3 * M * N * 4 + 4096 * 4, dtype=torch.uint8, device=dev)
             st = _lib.stream_ptr()
-            run = lambda: _lib.check(lib.dvd_gemm_bf16(_lib.ptr(Ah), _lib.ptr(Al), K, _lib.ptr(Wh), _lib.ptr(Wl), K, _lib.ptr(b), None, _lib.ptr(out),
-                                                       M, N, K, _lib.ptr(sk), sk.numel(), st), "gemm")
+
+            def run(Wh_=Wh, Wl_=Wl, out16=None, out32=out):
+                _lib.check(lib.dvd_gemm_bf16(_lib.ptr(Ah), _lib.ptr(Al), K, _lib.ptr(Wh_), _lib.ptr(Wl_), K, _lib.ptr(b), _lib.ptr(out16), _lib.ptr(out32),
+                                             M, N, K, _lib.stream_ptr()), "gemm")
             for _ in range(2 if check else 3):
                 run()
-            ts = []
-            for i in range(3 if check else 10):
-                flush.fill_(i)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); run(); e1.record(); e1.synchronize()
-                ts.append(e0.elapsed_time(e1) * 1e3)
+            torch.cuda.synchronize()
+            if graph:
+                # bf16 output like the pipeline's GEMMs; 8 weight copies (8 x 14 MB for the QKV shape) so that weights stream from HBM
+                R = 16
+                Ws = [(Wh.clone(), Wl.clone() if Wl is not None else None) for _ in range(8)]
+                outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(4)]
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for i in range(R):
+                        run(Ws[i % 8][0], Ws[i % 8][1], outs[i % 4], None)
+                g.replay(); torch.cuda.synchronize()
+                ts = []
+                for i in range(5):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); g.replay(); e1.record(); e1.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e3 / R)
+                run()
+            else:
+                ts = []
+                for i in range(3 if check else 10):
+                    flush.fill_(i)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); run(); e1.record(); e1.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e3)
             ts.sort()
             t = ts[len(ts) // 2]
             if mode == "bf16":
@@ -43,7 +67,6 @@ def main():
             else:
                 ref = A.double() @ W.double().t() + b.double()
             err = float((out.double() - ref).abs().max() / ref.abs().max())
-            assert int(sk[-4096 * 4:].view(torch.int32).abs().sum()) == 0, "split-K counters not left at zero"
             print(f"{tag:24s} {mode:7s} {name:18s} M={M:6d} N={N:5d} K={K:5d}  {t:7.1f} us  {2.0 * M * N * K / t / 1e6:7.1f} TF/s  relerr {err:.1e}", flush=True)
 
 
