@@ -13,8 +13,16 @@ import torch
 import torch.distributed as dist
 
 
+def _free_port() -> int:
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def setup_dist(backend: str | None = None):
-    """dist_util.py:21-41 without the MPI bootstrap.  Returns (rank, world, device)."""
+    """dist_util.py:21-41 without the MPI bootstrap.  Returns (rank, world, device).  Like the reference, a process group is ALWAYS
+    initialised (also for a single process), because val_TDiff.run() ends with an unconditional dist.barrier() (val_TDiff.py:115)."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
@@ -23,12 +31,20 @@ def setup_dist(backend: str | None = None):
         torch.cuda.set_device(dev)
     else:
         dev = torch.device("cpu")
-    if world > 1 and not dist.is_initialized():
+    if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29500")
+        if world == 1:
+            os.environ.setdefault("MASTER_PORT", str(_free_port()))
+        else:
+            os.environ.setdefault("MASTER_PORT", "29500")
         backend = backend or ("nccl" if dev.type == "cuda" else "gloo")
         dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, world, dev
+
+
+def load_state_dict(path, **kwargs):
+    """dist_util.py:53-63 without the MPI broadcast: every rank reads the file itself."""
+    return torch.load(path, **kwargs)
 
 
 def dev() -> torch.device:

@@ -53,8 +53,12 @@ def run_evaluation_docunet(settings, logger, val_loader, diffusion, model, pretr
                            pretrained_seg_model=None):
     os.makedirs(f"vis_hp/{settings.env.eval_dataset_name}/{settings.name}", exist_ok=True)
     dev = model.device
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # Documents are sharded over the ranks of an INITIALISED process group only (then gather_metrics really sees every rank's
+    # timings); the loader must be the reference's un-sharded one (val_TDiff.py:104) - with a DistributedSampler, pass shard=False.
+    import torch.distributed as tdist
+    shard = getattr(settings.env, "shard_documents", True) and tdist.is_available() and tdist.is_initialized()
+    rank = tdist.get_rank() if shard else 0
+    world = tdist.get_world_size() if shard else 1
     image_size = 64
     times = {}
     for i, data in enumerate(val_loader):

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for bn in 256 192 128; do for sp in 1 2 3; do echo "== bn=$bn sp=$sp"; DVD_GEMM_BN=$bn DVD_GEMM_SPLITS=$sp timeout 200 python tools/gemm_bench.py --graph 2>&1 | grep -v "x8 docs" ; done; done > gpurun_out/gemm_sweep.txt 2>&1
-cat gpurun_out/gemm_sweep.txt
+echo "== bench full"; timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_full.txt 2>&1; echo "rc=$?"; tail -c 7000 gpurun_out/bench_full.txt
+echo "== bench reference"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.txt 2>&1; echo "rc=$?"; tail -c 1500 gpurun_out/bench_ref.txt
