@@ -539,7 +539,10 @@ static int sample_group(const Ctx& c, const float* x_T, const float* init_flow0,
     // CM:597-598: while the rescaled t > 600 the model overrides init_feat with the un-warped feature.
     // GD:618-624: from the second iteration on, init_flow = previous pred_xstart and init_feat = warp(feat).
     // First iteration with t <= 600 (only possible for S < 3): the caller's init_feat (zeros at EV:167) is used.
-    int feat_mode = t_scaled_host[it] > 600.0f ? FEAT_ASIS : (it == 0 ? FEAT_EXPLICIT_OR_ZERO : FEAT_WARP);
+    // CM:599-601: with more than one sample per call, entries whose rescaled t equals 2 exactly also take the un-warped feature (the
+    // reference compares the float timestep with the integer label 2: only reachable at S = 1000, t index 2).
+    const bool asis = t_scaled_host[it] > 600.0f || (t_scaled_host[it] == 2.0f && n_hyp > 1);
+    int feat_mode = asis ? FEAT_ASIS : (it == 0 ? FEAT_EXPLICIT_OR_ZERO : FEAT_WARP);
     float* xn = s.xbuf[it & 1];
     float* pred = (it + 1 == S) ? final_flow : s.flow[cur ^ 1];      // pred of this step is init_flow of the next one
     DVD_TRY(denoise_step(c, x, s.flow[cur], feat_mode == FEAT_EXPLICIT_OR_ZERO ? init_feat0 : nullptr, n_hyp, feat_mode,

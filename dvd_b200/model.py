@@ -203,7 +203,7 @@ class DiT(nn.Module):
             t0 = float(t[0])
             tval = float(t0) if mode is not None else remap_t(t0)
             tab = eng.tables([tval])
-            feat_is_init = bool(t0 > 600 and iter is True)                  # cross_model.py:597-598
+            feat_is_init = bool(iter is True and (t0 > 600 or (N > 1 and bool((t == 2).all()))))     # cross_model.py:597-601
             if not feat_is_init and init_feat is None:
                 raise ValueError("init_feat is required when t <= 600")
             pred = torch.empty((N, 2, 64, 64), dtype=torch.float32, device=self._device)

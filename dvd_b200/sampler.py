@@ -9,6 +9,7 @@ is one more tiny kernel.  Nothing is computed with torch ops on the hot path.
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -108,8 +109,9 @@ class SpacedDiffusion:
 
         Extensions over the reference: ``shape[0]`` may be a batch of documents (the reference is
         limited to one); ``x_T`` supplies the initial noise explicitly ([docs*n_batch,2,64,64],
-        document-major).  When ``x_T`` is None the noise is drawn with the same two torch.randn calls as
-        gaussian_diffusion.py:559-569 so that a seeded run consumes the RNG identically."""
+        document-major).  When ``x_T`` is None the noise is drawn with the same torch.randn calls as
+        gaussian_diffusion.py:559-569 (and the S unused per-step draws of :479) so that a seeded run consumes the RNG identically
+        and a sequence of documents sees the same noise as under the reference."""
         if not isinstance(model, DiT):
             raise TypeError("dvd_b200 sampler drives dvd_b200.DiT only (no foreign-model path)")
         if eta != 0.0:
@@ -130,21 +132,111 @@ class SpacedDiffusion:
             if x_T is None:
                 _ = noise if noise is not None else torch.randn(*shape, device=dev)        # drawn, then discarded (GD:559-562)
                 x_T = torch.randn((docs * n_batch, *shape[1:]), device=dev)                # GD:569
+                for _ in range(self.num_timesteps):                                        # GD:479 draws randn_like(x) every step and
+                    torch.randn_like(x_T)                                                  # multiplies it by sigma = 0: keep the generator in step
             f = lambda v: v.to(device=dev, dtype=torch.float32).contiguous()
             x_T = f(x_T)
             assert tuple(x_T.shape) == (docs * n_batch, 2, 64, 64)
             eng = model.engine(docs, n_batch)
-            eng.static_forward(f(kw["y512"]), f(kw["mask_cat"]), f(kw["mask_y512"]), f(kw["line_msk"]))
             t_scaled, t_emb, a, b = self._plan()
             tables = eng.tables(t_emb)                    # cached on the packed weights (dropped by load_state_dict / .to())
             init_feat0 = kw.get("init_feat")
             if init_feat0 is not None and (t_scaled[0] > 600 or not bool(torch.any(init_feat0 != 0))):
                 init_feat0 = None
-            out = torch.empty((docs, 2, 64, 64), dtype=torch.float32, device=dev)
-            eng.sample(x_T, f(kw["init_flow"]), tables, t_scaled, a, b, None if init_feat0 is None else f(init_feat0), out)
+            inputs = {"y512": kw["y512"], "mask_cat": kw["mask_cat"], "mask_y512": kw["mask_y512"], "line_msk": kw["line_msk"],
+                      "x_T": x_T, "init_flow": kw["init_flow"]}
+            if init_feat0 is None and os.environ.get("DVD_NO_GRAPH", "0") != "1":
+                # the whole document (static conditioning + S steps + hypothesis mean: ~230 kernels) replays from ONE CUDA graph over
+                # static input buffers, like DewarpPipeline: per-call cost = six small device copies + one graph launch
+                g = self._graphed(eng, tables, t_scaled, a, b, docs, n_batch, dev)
+                out = g.run(inputs)
+            else:
+                eng.static_forward(f(kw["y512"]), f(kw["mask_cat"]), f(kw["mask_y512"]), f(kw["line_msk"]))
+                out = torch.empty((docs, 2, 64, 64), dtype=torch.float32, device=dev)
+                eng.sample(x_T, f(kw["init_flow"]), tables, t_scaled, a, b, None if init_feat0 is None else f(init_feat0), out)
             feat = eng.feat_nhwc().permute(0, 3, 1, 2).clone()    # detached from the workspace the next call overwrites
         final = {"sample": out, "pred_xstart": out, "feat_dict": feat}
         return out, final
+
+    @torch.no_grad()
+    def ddim_sample_loop_for_training(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, model_kwargs=None, device=None,
+                                      progress=False, eta=0.0, sampling_kwargs=None, logger=None, n_batch=1, time_variant=False, iter=True,
+                                      mode="train", timestep=None, pyramid=None, x_T=None):
+        """The no-grad roll-out inside ``training_losses_time_variant`` (gaussian_diffusion.py:647-780, called :924-942): DDIM steps
+        S-1 .. timestep+1 of ONE sample, with the RAW rescaled timestep embedded (``mode`` is not None, cross_model.py:575), returning
+        ``(clamp(pred_xstart), feat)``.  Same kernels as inference; only the step range and the timestep table differ."""
+        if not isinstance(model, DiT):
+            raise TypeError("dvd_b200 sampler drives dvd_b200.DiT only (no foreign-model path)")
+        if n_batch != 1 or eta != 0.0 or clip_denoised or denoised_fn is not None or time_variant is not True or iter is not True or mode is None:
+            raise NotImplementedError("roll-out implemented as called at gaussian_diffusion.py:924-942 (n_batch=1, eta=0, tv, iter, mode='train')")
+        if timestep is None or not (0 <= int(timestep) < self.num_timesteps - 1):
+            raise ValueError("timestep must be in [0, S-2] (the reference rolls out from S-1 down to timestep+1)")
+        kw = dict(model_kwargs or {})
+        dev = model.device
+        if dev.type != "cuda":
+            raise RuntimeError("dvd_b200 sampler has no CPU path: move the model to a CUDA device")
+        docs = int(shape[0])
+        assert docs == 1 and tuple(shape[1:]) == (2, 64, 64), shape
+        idx = list(range(int(timestep) + 1, self.num_timesteps))[::-1]                     # GD:723
+        with torch.cuda.device(dev):
+            if x_T is None:
+                _ = noise if noise is not None else torch.randn(*shape, device=dev)        # GD:718-721
+                x_T = torch.randn((n_batch, *shape[1:]), device=dev)                        # GD:728
+                for _ in idx:
+                    torch.randn_like(x_T)                                                  # GD:479 (unused, sigma = 0)
+            f = lambda v: v.to(device=dev, dtype=torch.float32).contiguous()
+            eng = model.engine(1, 1)
+            eng.static_forward(f(kw["y512"]), f(kw["mask_cat"]), f(kw["mask_y512"]), f(kw["line_msk"]))
+            t_scaled = [self.scaled_t(i) for i in idx]
+            ab = [self.ddim_ab(i) for i in idx]
+            tables = eng.tables(t_scaled)                                                  # raw timestep embedding (mode != None)
+            init_feat0 = kw.get("init_feat")
+            if init_feat0 is not None and (t_scaled[0] > 600 or not bool(torch.any(init_feat0 != 0))):
+                init_feat0 = None
+            out = torch.empty((1, 2, 64, 64), dtype=torch.float32, device=dev)
+            eng.sample(f(x_T), f(kw["init_flow"]), tables, t_scaled, [a for a, _ in ab], [b for _, b in ab],
+                       None if init_feat0 is None else f(init_feat0), out)
+            feat = eng.feat_nhwc().permute(0, 3, 1, 2).clone()
+        return out, feat
+
+    def _graphed(self, eng, tables, t_scaled, a, b, docs, n_batch, dev):
+        key = (id(eng), id(tables))
+        if getattr(self, "_fast", None) is None or self._fast[0] != key:
+            self._fast = (key, _GraphedDocument(eng, tables, t_scaled, a, b, docs, n_batch, dev))
+        return self._fast[1]
+
+
+class _GraphedDocument:
+    """Static input buffers + one CUDA graph of dvd_static_forward + dvd_sample for a fixed (engine, tables) pair."""
+
+    def __init__(self, eng, tables, t_scaled, a, b, docs, n_batch, dev):
+        self.eng, self.tables, self.t_scaled, self.a, self.b = eng, tables, t_scaled, a, b
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        self.buf = {"y512": z(docs, 3, 512, 512), "mask_cat": z(docs, 1, 512, 512), "mask_y512": z(docs, 384, 64, 64),
+                    "line_msk": z(docs, 64, 64, 64), "x_T": z(docs * n_batch, 2, 64, 64), "init_flow": z(docs, 2, 64, 64)}
+        self.out = z(docs, 2, 64, 64)
+        self.graph = None
+
+    def _enqueue(self):
+        bf = self.buf
+        self.eng.static_forward(bf["y512"], bf["mask_cat"], bf["mask_y512"], bf["line_msk"])
+        self.eng.sample(bf["x_T"], bf["init_flow"], self.tables, self.t_scaled, self.a, self.b, None, self.out)
+
+    def run(self, inputs) -> torch.Tensor:
+        for k, dst in self.buf.items():
+            src = inputs[k]
+            if tuple(src.shape) != tuple(dst.shape):
+                raise ValueError(f"{k}: expected shape {tuple(dst.shape)}, got {tuple(src.shape)}")
+            dst.copy_(src, non_blocking=True)
+        if self.graph is None:
+            self._enqueue()                                # eager warm-up (function attributes, driver entry points)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.graph = g
+        self.graph.replay()
+        return self.out.clone()
 
 
 def create_gaussian_diffusion(*, steps=1000, learn_sigma=False, sigma_small=False, noise_schedule="linear", use_kl=False,

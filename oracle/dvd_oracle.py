@@ -241,7 +241,7 @@ class Static:
 
 
 def denoiser_forward(sd, x, t_scaled: float, init_flow, init_feat, static: Static = None, *, y512=None, mask_cat=None,
-                     mask_y512=None, line_msk=None, as_written: bool = False):
+                     mask_y512=None, line_msk=None, as_written: bool = False, raw_t: bool = False):
     """CM:568-647 DiT.forward (mode=None, tv=True, iter=True, src_feat=None) -> (x0, feat).
 
     ``static`` may hold tensors for ONE document; they are broadcast over the N hypotheses
@@ -252,9 +252,10 @@ def denoiser_forward(sd, x, t_scaled: float, init_flow, init_feat, static: Stati
         static = Static(sd, y512, mask_cat, mask_y512, line_msk)
     rep = lambda v: v.expand(N, *v.shape[1:]) if v.shape[0] != N else v
     xe = patch_embed(sd, "obs", x)                                               # CM:571
-    temb = t_embed(sd, torch.full((N,), remap_t(t_scaled), dtype=torch.float32, device=x.device))  # CM:575-580
+    # CM:575-580: the strict-threshold remap only when mode is None; the training roll-out (mode='train') embeds the raw value
+    temb = t_embed(sd, torch.full((N,), t_scaled if raw_t else remap_t(t_scaled), dtype=torch.float32, device=x.device))
     feat = rep(static.feat)
-    if t_scaled > 600:                                                           # CM:597-598
+    if t_scaled > 600 or (N > 1 and t_scaled == 2.0):                            # CM:597-601 (entries whose float t equals the label 2)
         init_feat = feat
     r = patch_embed(sd, "r", torch.cat([init_flow, init_feat], dim=1))           # CM:602-603
     blocks = range(12) if as_written else (11,)
@@ -308,6 +309,24 @@ def sample(sd, inp: dict, S: int = 3, n_batch: int = 2, schedule: str = "cosine"
         img = ddim_update(sch, i, img, pred)                                      # GD:470-489
     out = torch.clamp(pred.mean(dim=0, keepdim=True), -1, 1)                     # GD:639-640, EV:137
     return (out, rec, feat) if record else out
+
+
+def rollout(sd, inp: dict, S: int = 3, timestep: int = 0, schedule: str = "cosine"):
+    """ddim_sample_loop_for_training (GD:647-780) as called by training_losses_time_variant (GD:924-942): one sample, DDIM steps
+    S-1 .. timestep+1, raw timestep embedding (mode='train'), returns clamp(pred_xstart).  ``inp['x_T'][:1]`` is the initial noise."""
+    sch = Schedule(S, schedule)
+    img = inp["x_T"][:1].clone()
+    init_flow, init_feat = inp["init_flow"].clone(), inp["init_feat"].clone()
+    static = Static(sd, inp["y512"], inp["mask_cat"], inp["mask_y512"], inp["line_msk"])
+    b64 = base_grid(64)
+    pred = feat = None
+    for i in range(S - 1, timestep, -1):                                         # GD:723
+        if i != S - 1:                                                           # GD:738-759
+            init_flow = pred.clone()
+            init_feat = grid_sample_ref(feat, (init_flow + b64) * 2 - 1)
+        pred, feat = denoiser_forward(sd, img, sch.scaled_t(i), init_flow, init_feat, static, raw_t=True)
+        img = ddim_update(sch, i, img, pred)
+    return torch.clamp(pred, -1, 1)
 
 
 # ----------------------------------------------------------------------------- unwarp (EV:300-306 + WP:73)

@@ -436,6 +436,22 @@ def test_sampling_bf16_within_stated_bound(dev, models, golden_dir, doc):
     assert float(d.mean()) < BF16_MEAN and float(d.max()) < BF16_MAX, (float(d.mean()), float(d.max()))
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_training_rollout_matches_reference_golden(dev, models, golden_dir, prec):
+    """ddim_sample_loop_for_training (gaussian_diffusion.py:647-780; raw timestep embedding, steps S-1 .. timestep+1,
+    one sample) against the unmodified reference's output."""
+    g = np.load(os.path.join(golden_dir, "rollout_doc0_t0.npz"))
+    inp = synth.make_doc_inputs(0, H=96, W=128)
+    kw = {k: inp[k] for k in ("init_flow", "y512", "mask_cat", "init_feat", "mask_y512", "line_msk")}
+    out, feat = _diffusion().ddim_sample_loop_for_training(models[prec], (1, 2, 64, 64), noise=None, clip_denoised=False, model_kwargs=kw,
+                                                            eta=0.0, progress=True, n_batch=1, time_variant=True, iter=True, mode="train",
+                                                            timestep=0, x_T=inp["x_T"][:1])
+    torch.cuda.synchronize()
+    d = (out.cpu() - torch.from_numpy(g["pred"])).abs()
+    assert float(d.mean()) < FP32_MEAN and float(d.max()) < FP32_MAX, (float(d.mean()), float(d.max()))
+    np.testing.assert_allclose(feat.cpu()[:, ::16, ::4, ::4].numpy(), g["feat_sub"], atol=2e-4, rtol=1e-3)
+
+
 def test_sampling_S10_thresholds_fp32(dev, models, golden_dir):
     """S = 10 hits t = 600.0 and 300.0 exactly (strict thresholds of cross_model.py:576-579)."""
     g = np.load(os.path.join(golden_dir, "sample_S10_doc2.npz"))
@@ -491,13 +507,19 @@ def test_pipeline_device_host_and_pipelined_submission_agree(dev, models):
 
 
 def test_seeded_noise_consumption_matches_reference_order(dev, models):
-    """Without x_T the sampler draws randn(shape) then randn(n_batch, ...) like gaussian_diffusion.py:559-569."""
+    """Without x_T the sampler draws randn(shape) then randn(n_batch, ...) like gaussian_diffusion.py:559-569, and leaves the
+    generator where the reference leaves it (one unused randn_like(x) per DDIM step, gaussian_diffusion.py:479), so that the NEXT
+    document of a seeded run sees the same noise too."""
     inp = synth.make_doc_inputs(0, with_photo=False)
     torch.manual_seed(123); torch.cuda.manual_seed(123)
     _ = torch.randn(1, 2, 64, 64, device=dev); xT = torch.randn(2, 2, 64, 64, device=dev)
+    for _ in range(3):
+        torch.randn_like(xT)
+    nxt = torch.randn(8, device=dev)
     torch.manual_seed(123); torch.cuda.manual_seed(123)
     a, _ = _diffusion().ddim_sample_loop(models["fp32"], (1, 2, 64, 64), clip_denoised=False, model_kwargs=_kwargs(inp), eta=0.0,
                                          n_batch=2, time_variant=True)
+    assert torch.equal(torch.randn(8, device=dev), nxt)
     b, _ = _diffusion().ddim_sample_loop(models["fp32"], (1, 2, 64, 64), clip_denoised=False, model_kwargs=_kwargs(inp), eta=0.0,
                                          n_batch=2, time_variant=True, x_T=xT)
     assert torch.equal(a, b)

@@ -107,6 +107,15 @@ def test_sampling_S10_thresholds(golden_dir, state_dict_live):
     assert np.abs(out.numpy() - g["sample"]).max() < 5e-4
 
 
+def test_training_rollout_matches_reference(golden_dir, state_dict_live):
+    """the no-grad roll-out of training_losses_time_variant (gaussian_diffusion.py:647-780), golden from the
+    unmodified reference (oracle/make_golden_rollout.py)."""
+    g = _load(golden_dir, "rollout_doc0_t0.npz")
+    with torch.no_grad():
+        out = O.rollout(state_dict_live, synth.make_doc_inputs(0, H=96, W=128), S=3, timestep=0)
+    assert float((out - torch.from_numpy(g["pred"])).abs().max()) < 2e-5
+
+
 @pytest.mark.parametrize("case", ["sampled_page", "smooth_noise", "adversarial_noise", "zero_page_1ch"])
 def test_unwarp_matches_reference(golden_dir, case):
     u = _load(golden_dir, "unwarp.npz")

@@ -129,6 +129,10 @@ def test_val_tdiff_dropin_matches_the_unmodified_script_on_gpu(tmp_path, monkeyp
     monkeypatch.setenv("DVD_PRECISION", "bf16x3")
     ck, data = _make_workspace(tmp_path, n_docs=2, H=480, W=640)
     os.makedirs(tmp_path / "vis_hp" / "debug_vis", exist_ok=True)          # the reference's debug dumps (gaussian_diffusion.py:606,614)
+    # evaluation.py:152 constructs a torchvision VGG16 with pretrained weights (a download) that the default config never uses
+    import torchvision
+    vgg16 = torchvision.models.vgg16
+    monkeypatch.setattr(torchvision.models, "vgg16", lambda *a, **k: vgg16(weights=None))
     torch.backends.cudnn.allow_tf32 = False                                 # strict fp32 reference (default would run its convs in TF32)
     torch.backends.cuda.matmul.allow_tf32 = False
     outs = {}
