@@ -201,11 +201,16 @@ class DewarpPipeline:
                      "other": 1.0 - sum(tot_ms) / tot, "denoiser_ms_per_step": tot / n}
             gemm_tf = fl[0] / (tot_ms[0] / n * 1e-3) / 1e12 if tot_ms[0] > 0 else 0.0
             attn_tf = fl[1] / (tot_ms[1] / n * 1e-3) / 1e12 if tot_ms[1] > 0 else 0.0
+            try:
+                traffic = json.load(open(os.path.join(os.path.dirname(peaks_path), "profiles", "r2_traffic.json")))
+            except Exception:
+                traffic = {}
             tensor_mode = self.precision in ("bf16", "bf16x3")
             passes = 3 if self.precision == "bf16x3" else 1
             peak_tf = peaks["bf16_tflops_sustained"] if tensor_mode else 72.0      # fp32 FFMA: 148 SM x 128 FMA x 2 x 1.9 GHz
             roof = {"kernel": "k_gemm_pair: dense GEMM (all linear layers of one step batch)", "bound": "tensor", "achieved": gemm_tf,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": None,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
+                    "traffic": (traffic.get("gemm_dominant") if self.precision == "bf16x3" else None),
                     "launches_per_step": int(ln[0]), "gflop_per_step": fl[0] / 1e9, "attention_tflops": attn_tf,
                     "attention_gflop_per_step": fl[1] / 1e9,
                     # achieved / frac count ALGORITHMIC flops (2 M N K).  The split-precision mode executes three tensor-core passes per
@@ -255,7 +260,8 @@ class DewarpPipeline:
             t8_noise = time_unwarp(d["photo_u8"], "dvd_unwarp_u8", self.map64)
             gb32, gb8 = 24.0 * px / 1e9, 6.0 * px / 1e9
             ru = {"kernel": "k_unwarp_tma fp32 NCHW (24 B/px)", "map": "smooth synthetic warp, amplitude 0.02", "bound": "hbm", "achieved": gb32 / (t32 * 1e-3), "peak": peaks["hbm_gbs"],
-                  "unit": "GB/s", "frac": gb32 / (t32 * 1e-3) / peaks["hbm_gbs"], "traffic": None, "ms": t32,
+                  "unit": "GB/s", "frac": gb32 / (t32 * 1e-3) / peaks["hbm_gbs"],
+                  "traffic": (traffic.get("unwarp_f32_1500x2000") if (self.H, self.W) == (1500, 2000) else None), "ms": t32,
                   "u8_variant": {"achieved": gb8 / (t8 * 1e-3), "frac": gb8 / (t8 * 1e-3) / peaks["hbm_gbs"], "ms": t8, "bytes_per_px": 6},
                   "random_init_map": {"note": "the map sampled with random-init weights is white noise", "ms_f32": t32_noise, "ms_u8": t8_noise},
                   "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % which}

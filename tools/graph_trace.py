@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
-    model = DiT(precision="bf16")
+    model = DiT(precision=os.environ.get("DVD_PRECISION", "bf16x3"))
     model.load_state_dict(synth.make_state_dict(1234, live_only=True), strict=False)
     model.to(dev)
     pipe = DewarpPipeline(model, diffusion_steps=3, n_batch=2, docs=a.docs, height=a.height, width=a.width)
