@@ -11,6 +11,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "misc.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -27,6 +28,8 @@ struct Workspace {
   float* final_flow;                       // [docs * n_hyp, 2, 64, 64]: last pred_xstart of every hypothesis (input of the mean)
   // 16-bit GEMM operand staging (tensor modes): plain bf16, or bf16 hi + lo pairs in DVD_PREC_BF16X3
   B16 a_stat16, ctx16[3], a_r16, r16, qn16, xo16, hmod16, h116, hd16, att_d16, f116, f216;
+  B16 X16;                                 // decoder residual stream as a GEMM operand (fused-LayerNorm path, DVD_PREC_BF16X3)
+  float* lnstats;                          // [M][48][2] partial row statistics of X for the LayerNorm fused into the next GEMM
   // attention operands: bf16 (DVD_PREC_BF16) or fp16 (DVD_PREC_BF16X3)
   __nv_bfloat16 *q16, *kv_static16[3], *kv_r16, *qkv16, *qkv_d16;       // Q, K row-major
   __nv_bfloat16 *vt_static16[3], *vt_r16, *vt_qkv16, *vt_d16;            // V^T [sample, C_v, 1024] written by the GEMM epilogues
@@ -89,6 +92,7 @@ static void carve_step(Carver& k, Workspace& w, int docs, int n_hyp, bool tc, bo
     w.f216 = k.P(M * 2048, x3);
     w.q16 = k.H(M * 384); w.kv_r16 = k.H(M * 768); w.qkv16 = k.H(4 * M * 1152); w.qkv_d16 = k.H(M * 4608);
     w.vt_r16 = k.H(M * 384); w.vt_qkv16 = k.H(4 * M * 384); w.vt_d16 = k.H(M * 1536);
+    if (x3) { w.X16 = k.P(M * 1536, true); w.lnstats = k.F(M * 48 * 2); }
   }
 }
 
@@ -295,6 +299,11 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
   const dvd_weights_t& w = *c.w; const Workspace& s = c.ws; cudaStream_t st = c.st;
   const int N = c.docs * c.n_hyp, M = N * 1024;
   const bool tc = c.tc();
+  // DVD_LN_FUSION=1 (opt-in): LayerNorm folded into the decoder GEMMs.  Measured on B200 (profiles/r2_ln_fusion.txt): 370 fewer
+  // launches per 10 documents but 171 vs 178 docs/s at batch 1 (the longer epilogues sit on the exposed tail of each GEMM), equal
+  // at 16 documents in flight, so the separate LayerNorm kernels stay the default.
+  const int want_lnf = getenv("DVD_LN_FUSION") ? atoi(getenv("DVD_LN_FUSION")) : 0;
+  const bool lnf = c.x3() && want_lnf && w.dec[0].qkv_ln.bf16 && w.dec[0].qkv_ln.bf16_lo;
   const float* ada = trow + 384;                 // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
   const float* fin = trow + 384 + 2304;          // shift[1536], scale[1536]
   auto off16 = [](const B16& b, size_t n) { B16 r; r.hi = b.hi + n; r.lo = b.lo ? b.lo + n : nullptr; return r; };
@@ -372,34 +381,51 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     // h- and w-branch side by side: conv1x1 + ReLU, then conv1x1 + sigmoid (CA:143-157)
     DVD_TRY(gemv_pair(mean, mean, 1536, w.h_scale0.f32, w.w_scale0.f32, w.h_scale0_b, w.w_scale0_b, hs1, ws1, 1536, N, 1536, 1536, 1, st));
     DVD_TRY(gemv_pair(hs1, ws1, 1536, w.h_scale2.f32, w.w_scale2.f32, w.h_scale2_b, w.w_scale2_b, hs, wsv, 1536, N, 1536, 1536, 3, st));
-    DVD_TRY(posenc_add(s.X, hs, wsv, w.dec_hpe, w.dec_wpe, N, 1536, st));
+    // DVD_LN_FUSION=1: the decoder's twelve LayerNorms are folded into the GEMMs that consume them (no LN kernel, no normalised copy):
+    // every producer of the residual stream X also writes X as an operand pair and the rows' partial (sum, sum of squares); the QKV /
+    // conv1 GEMMs multiply the RAW rows by gamma-scaled weights and normalise in the epilogue (Epilogue::ln_*).  Accuracy checked on
+    // the oracle first (oracle/precision_study.py --ln-fusion: 1.44e-6 -> 1.53e-6 mean map error).
+    if (lnf) DVD_TRY(posenc_add_ln(s.X, hs, wsv, w.dec_hpe, w.dec_wpe, N, 1536, s.X16.hi, s.X16.lo, s.lnstats, 48, st));
+    else DVD_TRY(posenc_add(s.X, hs, wsv, w.dec_hpe, w.dec_wpe, N, 1536, st));
   }
   if (g_stop_after == 2) return 0;
   // ---- 6 decoder layers (CA:377-396)
   for (int l = 0; l < 6; ++l) {
     const dvd_dec_layer_t& L = w.dec[l];
-    DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n1_w, L.n1_b, nullptr, nullptr, st));
+    if (!lnf) DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n1_w, L.n1_b, nullptr, nullptr, st));
     {
       Epilogue e; e.out = tc ? nullptr : s.qkv_d; e.ldc = 4608;
       if (tc) { out_attn(c, e, s.qkv_d16, 4608); e.vt_out = s.vt_d16; e.vt_col0 = 3072; }
-      DVD_TRY(linear(c, s.hd, s.hd16, 1536, L.qkv, 0, M, 4608, e));
+      if (lnf) {
+        e.ln_stats = s.lnstats; e.ln_colsum = L.qkv_colsum; e.ln_chunks = 48; e.ln_eps = 1e-5f; e.bias = L.qkv_cvec;
+        DVD_TRY(linear(c, nullptr, s.X16, 1536, L.qkv_ln, 0, M, 4608, e));
+      } else {
+        DVD_TRY(linear(c, s.hd, s.hd16, 1536, L.qkv, 0, M, 4608, e));
+      }
     }
     DVD_TRY(attention(c, s.qkv_d, s.qkv_d16, 4608, s.qkv_d + 1536, tc ? s.qkv_d16 + 1536 : nullptr, 4608, s.qkv_d + 3072, s.vt_d16, 4608,
                       s.att_d, s.att_d16, 1536, N, 256, 0.0625f, 1));
     {
       Epilogue e; e.resid = s.X; e.ldr = 1536; e.out = s.X; e.ldc = 1536;
+      if (lnf) { out_operand(e, s.X16, 1536); e.stats_out = s.lnstats; }
       DVD_TRY(linear(c, s.att_d, s.att_d16, 1536, L.fc, 0, M, 1536, e));
     }
-    DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n2_w, L.n2_b, nullptr, nullptr, st));
+    if (!lnf) DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n2_w, L.n2_b, nullptr, nullptr, st));
     {
       Epilogue e; e.scale = L.bn1_scale; e.shift = L.bn1_shift; e.act = ACT_RELU; e.out = tc ? nullptr : s.f1; e.ldc = 2048;
       if (tc) out_operand(e, s.f116, 2048);
-      DVD_TRY(linear(c, s.hd, s.hd16, 1536, L.conv1, 0, M, 2048, e));
+      if (lnf) {
+        e.ln_stats = s.lnstats; e.ln_colsum = L.conv1_colsum; e.ln_chunks = 48; e.ln_eps = 1e-5f; e.bias = L.conv1_cvec;
+        DVD_TRY(linear(c, nullptr, s.X16, 1536, L.conv1_ln, 0, M, 2048, e));
+      } else {
+        DVD_TRY(linear(c, s.hd, s.hd16, 1536, L.conv1, 0, M, 2048, e));
+      }
     }
     if (tc) DVD_TRY(dwconv3x3_bn_relu_bf16(s.f116.hi, s.f116.lo, L.dw_w, L.bn2_scale, L.bn2_shift, s.f216.hi, s.f216.lo, N, 2048, st));
     else DVD_TRY(dwconv3x3_bn_relu(s.f1, L.dw_w, L.bn2_scale, L.bn2_shift, s.f2, nullptr, N, 2048, st));
     {
       Epilogue e; e.scale = L.bn3_scale; e.shift = L.bn3_shift; e.act = ACT_RELU; e.resid = s.X; e.ldr = 1536; e.out = s.X; e.ldc = 1536;
+      if (lnf) { out_operand(e, s.X16, 1536); e.stats_out = s.lnstats; }
       DVD_TRY(linear(c, s.f2, s.f216, 2048, L.conv2, 0, M, 1536, e));
     }
     if (g_stop_after == 3 + l) return 0;

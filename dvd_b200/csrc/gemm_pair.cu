@@ -14,9 +14,9 @@
 //     across units; transaction bytes of both CTAs are counted on the LEADER's full barrier.
 //   * warp 1 (one lane, leader)     MMA issuer: 4 (or 12: hi*hi, lo*hi, hi*lo) UMMA 256 x BN x 16 per stage into one of TWO TMEM
 //     accumulators; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs.
-//   * warps 2..9 (both CTAs)        epilogue of the CTA's own 128 rows, overlapping the next unit's main loop: each warp owns a TMEM
-//     lane quarter x half of the columns; tcgen05.ld 32x32 -> private XOR-swizzled 4 KB staging tile -> row-coalesced fused epilogue
-//     (8 lanes per 128-byte row segment).
+//   * warps 4..11 (both CTAs)       epilogue of the CTA's own 128 rows, overlapping the next unit's main loop: each warp owns a TMEM
+//     lane quarter x half of the columns; tcgen05.ld 16x256b (mma-fragment layout: a quad holds one 32-byte sector of a row) -> fused
+//     epilogue in registers -> sector-complete global accesses, no shared-memory staging.
 //   * CONV: A is an NHWC activation read through a 4-D tensor map (implicit GEMM of the 3x3 pyramid convolutions, zero padding = TMA
 //     out-of-bounds fill); a pair covers 256 consecutive pixels of one image row.
 #include "gemm_tc.cuh"
@@ -28,8 +28,15 @@ namespace dvd {
 using namespace tc;
 
 constexpr int PBM = 128, PBK = 64;
-constexpr int PP_THREADS = 320;           // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+// 12 warps = 3 warpgroups: warpgroup 0 = {warp 0: TMA producer, warp 1: MMA issuer, warps 2-3: idle}, warpgroups 1-2 = 8 epilogue warps.
+// The kernel is launched with 168 registers per thread (65536 / 384); after the set-up the first warpgroup gives registers back
+// (setmaxnreg.dec 56) and the epilogue warpgroups take them (setmaxnreg.inc 224): their software-pipelined epilogue (accumulator fragment +
+// two sets of prefetched residual / pos-embed / column vectors) spilled ~1 KB per thread under the flat 168-register budget.
+constexpr int PP_THREADS = 384;
+constexpr int PP_EPI_WARP0 = 4;           // first epilogue warp
 constexpr int PP_EPI_WARPS = 8;
+constexpr int PP_REGS_CTRL = 56, PP_REGS_EPI = 224;
+static_assert(128 * PP_REGS_CTRL + 256 * PP_REGS_EPI <= 65536, "register budget after setmaxnreg");
 
 template <int BN, bool X3>
 struct PairCfg {
@@ -38,8 +45,7 @@ struct PairCfg {
   static constexpr int B_BYTES = (BN / 2) * PBK * 2;            // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int B_OFF = NOP * A_BYTES;
-  static constexpr int STAGING_BYTES = PP_EPI_WARPS * 32 * 32 * 4;   // one 32 x 32 fp32 tile per epilogue warp
-  static constexpr int FIXED = STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int FIXED = 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int STAGES_FIT = (232448 - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
@@ -110,7 +116,7 @@ __device__ __forceinline__ unsigned long long ptime() { unsigned long long t; as
 #define PTRACE(slot) do { } while (0)
 #endif
 #ifdef DVD_GEMM_TRACE2      // epilogue detail of (unit 0, chunk 0, warp 2) in slots 7..12 (single-unit shapes only)
-#define ETRACE(slot) do { if (warp == 2 && lane == 0 && it == 0 && ch == 0) PTRACE(slot); } while (0)
+#define ETRACE(slot) do { if (warp == PP_EPI_WARP0 && lane == 0 && it == 0 && ch == 0) PTRACE(slot); } while (0)
 #else
 #define ETRACE(slot) do { } while (0)
 #endif
@@ -118,72 +124,161 @@ __device__ __forceinline__ unsigned long long ptime() { unsigned long long t; as
 // ---- specialised epilogue bodies.  The generic Epilogue is a bag of run-time options; evaluating them per row costs ~600 warp
 // instructions per 32 x 32 chunk, and with two epilogue warps per scheduler the epilogue of a 128 x 256 tile took 10 us (measured
 // with tools/gemm_trace.py --epi).  The host classifies the Epilogue into a (flags, output kind) key; the combinations the denoiser
-// uses are compiled as straight-line code (~150 instructions per chunk), anything else takes the generic path.
-enum { EF_SCALE = 1, EF_FLOOR = 2, EF_GATE = 4, EF_POS = 8, EF_RES = 16, EF_GELU = 32, EF_GELUX = 64 };
-enum { EO_F32 = 0, EO_BF16 = 1, EO_PAIR = 2, EO_F16 = 3 };
+// uses are compiled as straight-line code, anything else takes the generic path.
+enum { EF_SCALE = 1, EF_FLOOR = 2, EF_GATE = 4, EF_POS = 8, EF_RES = 16, EF_GELU = 32, EF_GELUX = 64, EF_LN = 128 };
+// EO_F32X: fp32 residual stream + its 16-bit operand copy (bf16, or a pair when out_lo is set) + per-row partial statistics for a
+// LayerNorm fused into the next GEMM
+enum { EO_F32 = 0, EO_BF16 = 1, EO_PAIR = 2, EO_F16 = 3, EO_F32X = 4 };
 constexpr int EPI_GENERIC = -1;
-__host__ __device__ constexpr int epi_key(int flags, int out) { return (flags << 2) | out; }
+__host__ __device__ constexpr int epi_key(int flags, int out) { return (flags << 3) | out; }
 
-struct EpiRowCtx { int col, prow, res_row0, pos_row0, orow0, ocol_add, N; };
+struct LnRows { float m[4], rs[4]; };   // mean / rstd of this thread's four rows (fused-LN consumers)
 
-template <int F, int O>
-__device__ __forceinline__ void epi_rows(const Epilogue& e, const float4 (&a)[8], const EpiRowCtx& c) {
-  const float4 cb = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + c.col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), ct = make_float4(0.f, 0.f, 0.f, 0.f), cg = cs;
-  if (F & EF_SCALE) { cs = __ldg(reinterpret_cast<const float4*>(e.scale + c.col)); ct = __ldg(reinterpret_cast<const float4*>(e.shift + c.col)); }
-  if (F & EF_GATE) cg = __ldg(reinterpret_cast<const float4*>(e.gate + c.col));
-  float4 qv[8], pv[8];
-  if (F & EF_RES) {
-    const float* rp = e.resid + (size_t)(c.res_row0 + c.prow) * e.ldr + c.col;       // may alias e.out (in-place residual)
+// Register-fragment epilogue.  tcgen05.ld.16x256b.x4 hands a warp 16 TMEM lanes x 32 columns in the mma-fragment layout: thread t holds, for
+// each 8-column block j, columns 8j + 2(t%4) + {0,1} of lanes t/4 and t/4 + 8.  Two loads (lanes +0 and +16) cover the warp's 32 lanes, so a
+// thread owns rows t/4 + 8i (i = 0..3) x 4 column pairs.  A quad then holds 8 consecutive columns of a row = one 32-byte sector of an fp32
+// output / residual row, so the global accesses are sector-complete WITHOUT a shared-memory transpose: no staging tile, no warp syncs,
+// and the ring gets the 32 KB back.  (The first version staged through XOR-swizzled shared memory: 1.5 us per 32x32 chunk, see
+// profiles/r2_gemm_trace_*.txt.)
+struct EpiRowCtx { int col0, res_row0, pos_row0, orow0, ocol_add, N; };      // col0: first column of the chunk; *_row0: of the warp's 32 rows
+
+struct Frag { uint32_t a[16], b[16]; };       // a: lanes 0..15 of the quarter, b: lanes 16..31
+__device__ __forceinline__ float2 frag_val(const Frag& f, int i, int j) {     // row t/4 + 8i, columns 8j + 2(t%4) + {0,1}
+  const uint32_t* r = (i < 2) ? f.a : f.b;
+  const int o = 4 * j + 2 * (i & 1);
+  return make_float2(__uint_as_float(r[o]), __uint_as_float(r[o + 1]));
+}
+
+// Everything the epilogue of one 32 x 32 chunk READS from global memory (per-column vectors, residual, pos-embed).  None of it depends on
+// the accumulator, so the loads of chunk ch+1 are issued before chunk ch is processed (and those of a unit's first chunk before the
+// wait for the accumulator): the L2 latency of the bias / residual fetch (~0.5 us, it used to be paid once per chunk and warp) is hidden.
+template <int F>
+struct EpiLoads {
+  float2 cb[4], cs[4], ct[4], cg[4], cl[4];
+  float2 qv[4][4], pv[4][4];
+};
+template <int F>
+__device__ __forceinline__ void epi_load(const Epilogue& e, const EpiRowCtx& c, int lane, EpiLoads<F>& L) {
+  const int tr = lane >> 2, tc2 = 2 * (lane & 3);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) qv[i] = *reinterpret_cast<const float4*>(rp + (size_t)(i * 4) * e.ldr);
+  for (int j = 0; j < 4; ++j) {
+    const int col = c.col0 + 8 * j + tc2;
+    L.cb[j] = e.bias ? __ldg(reinterpret_cast<const float2*>(e.bias + col)) : make_float2(0.f, 0.f);
+    if (F & EF_SCALE) { L.cs[j] = __ldg(reinterpret_cast<const float2*>(e.scale + col)); L.ct[j] = __ldg(reinterpret_cast<const float2*>(e.shift + col)); }
+    if (F & EF_GATE) L.cg[j] = __ldg(reinterpret_cast<const float2*>(e.gate + col));
+    if (F & EF_LN) L.cl[j] = __ldg(reinterpret_cast<const float2*>(e.ln_colsum + col));
+  }
+  if (F & EF_RES) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* rp = e.resid + (size_t)(c.res_row0 + tr + 8 * i) * e.ldr + c.col0 + tc2;       // may alias e.out (in-place residual)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) L.qv[i][j] = *reinterpret_cast<const float2*>(rp + 8 * j);
+    }
   }
   if (F & EF_POS) {
-    const float* pp = e.pos + (size_t)(c.pos_row0 + c.prow) * c.N + c.col;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pv[i] = __ldg(reinterpret_cast<const float4*>(pp + (size_t)(i * 4) * c.N));
+    for (int i = 0; i < 4; ++i) {
+      const float* pp = e.pos + (size_t)(c.pos_row0 + tr + 8 * i) * c.N + c.col0 + tc2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) L.pv[i][j] = __ldg(reinterpret_cast<const float2*>(pp + 8 * j));
+    }
   }
-  const size_t o0 = (size_t)(c.orow0 + c.prow) * (O == EO_F32 ? e.ldc : e.ldc_bf16) + c.col + c.ocol_add;
-  const size_t ostep = (size_t)4 * (O == EO_F32 ? e.ldc : e.ldc_bf16);
+}
+
+template <int F, int O>
+__device__ __forceinline__ void epi_rows(const Epilogue& e, const Frag& f, const EpiRowCtx& c, int lane, const EpiLoads<F>& L, const LnRows& ln) {
+  const int tr = lane >> 2, tc2 = 2 * (lane & 3);
+  const int ld = (O == EO_F32 || O == EO_F32X) ? e.ldc : e.ldc_bf16;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float v[4] = {a[i].x + cb.x, a[i].y + cb.y, a[i].z + cb.z, a[i].w + cb.w};
-    if (F & EF_SCALE) { v[0] = v[0] * cs.x + ct.x; v[1] = v[1] * cs.y + ct.y; v[2] = v[2] * cs.z + ct.z; v[3] = v[3] * cs.w + ct.w; }
-    if (F & EF_FLOOR) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-    if (F & EF_GELU) { v[0] = gelu_tanh_fast(v[0]); v[1] = gelu_tanh_fast(v[1]); v[2] = gelu_tanh_fast(v[2]); v[3] = gelu_tanh_fast(v[3]); }
-    if (F & EF_GELUX) { v[0] = gelu_tanh(v[0]); v[1] = gelu_tanh(v[1]); v[2] = gelu_tanh(v[2]); v[3] = gelu_tanh(v[3]); }
-    if (F & EF_POS) { v[0] += pv[i].x; v[1] += pv[i].y; v[2] += pv[i].z; v[3] += pv[i].w; }
-    if (F & EF_GATE) { v[0] *= cg.x; v[1] *= cg.y; v[2] *= cg.z; v[3] *= cg.w; }
-    if (F & EF_RES) { v[0] += qv[i].x; v[1] += qv[i].y; v[2] += qv[i].z; v[3] += qv[i].w; }
-    const size_t off = o0 + i * ostep;
-    if (O == EO_F32) {
-      *reinterpret_cast<float4*>(e.out + off) = make_float4(v[0], v[1], v[2], v[3]);
-    } else if (O == EO_PAIR) {
-      uint2 uu, ll;
-      split_bf16x2(v[0], v[1], uu.x, ll.x);
-      split_bf16x2(v[2], v[3], uu.y, ll.y);
-      *reinterpret_cast<uint2*>(e.out_bf16 + off) = uu;
-      *reinterpret_cast<uint2*>(e.out_lo + off) = ll;
-    } else if (O == EO_F16) {
-      *reinterpret_cast<uint2*>(e.out_bf16 + off) = make_uint2(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]));
-    } else {
-      *reinterpret_cast<uint2*>(e.out_bf16 + off) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  for (int i = 0; i < 4; ++i) {
+    const size_t o0 = (size_t)(c.orow0 + tr + 8 * i) * ld + c.col0 + tc2 + c.ocol_add;
+    float s1 = 0.f, s2 = 0.f;                                  // EO_F32X: this thread's share of the row's chunk statistics
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 a = frag_val(f, i, j);
+      if (F & EF_LN) { a.x = ln.rs[i] * (a.x - ln.m[i] * L.cl[j].x); a.y = ln.rs[i] * (a.y - ln.m[i] * L.cl[j].y); }
+      float v0 = a.x + L.cb[j].x, v1 = a.y + L.cb[j].y;
+      if (F & EF_SCALE) { v0 = v0 * L.cs[j].x + L.ct[j].x; v1 = v1 * L.cs[j].y + L.ct[j].y; }
+      if (F & EF_FLOOR) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+      if (F & EF_GELU) { v0 = gelu_tanh_fast(v0); v1 = gelu_tanh_fast(v1); }
+      if (F & EF_GELUX) { v0 = gelu_tanh(v0); v1 = gelu_tanh(v1); }
+      if (F & EF_POS) { v0 += L.pv[i][j].x; v1 += L.pv[i][j].y; }
+      if (F & EF_GATE) { v0 *= L.cg[j].x; v1 *= L.cg[j].y; }
+      if (F & EF_RES) { v0 += L.qv[i][j].x; v1 += L.qv[i][j].y; }
+      const size_t off = o0 + 8 * j;
+      if (O == EO_F32X) {
+        *reinterpret_cast<float2*>(e.out + off) = make_float2(v0, v1);
+        const size_t off16 = (size_t)(c.orow0 + tr + 8 * i) * e.ldc_bf16 + c.col0 + tc2 + c.ocol_add + 8 * j;
+        if (e.out_lo) {
+          uint32_t hi, lo;
+          split_bf16x2(v0, v1, hi, lo);
+          *reinterpret_cast<uint32_t*>(e.out_bf16 + off16) = hi;
+          *reinterpret_cast<uint32_t*>(e.out_lo + off16) = lo;
+        } else {
+          *reinterpret_cast<uint32_t*>(e.out_bf16 + off16) = pack_bf16x2(v0, v1);
+        }
+        s1 += v0 + v1; s2 += v0 * v0 + v1 * v1;
+      } else if (O == EO_F32) {
+        *reinterpret_cast<float2*>(e.out + off) = make_float2(v0, v1);
+      } else if (O == EO_PAIR) {
+        uint32_t hi, lo;
+        split_bf16x2(v0, v1, hi, lo);
+        *reinterpret_cast<uint32_t*>(e.out_bf16 + off) = hi;
+        *reinterpret_cast<uint32_t*>(e.out_lo + off) = lo;
+      } else if (O == EO_F16) {
+        *reinterpret_cast<uint32_t*>(e.out_bf16 + off) = pack_f16x2(v0, v1);
+      } else {
+        *reinterpret_cast<uint32_t*>(e.out_bf16 + off) = pack_bf16x2(v0, v1);
+      }
+    }
+    if (O == EO_F32X) {
+      // the quad holds the 32 columns of this chunk of row tr + 8i: fixed-order butterfly, then one (sum, sum of squares) per chunk
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+      if ((lane & 3) == 0)
+        *reinterpret_cast<float2*>(e.stats_out + ((size_t)(c.orow0 + tr + 8 * i) * (c.N >> 5) + ((c.col0 + c.ocol_add) >> 5)) * 2) = make_float2(s1, s2);
     }
   }
 }
 
 // any other Epilogue: run-time options (kept out of line: it is not on the denoiser's path)
-__device__ __noinline__ void epi_rows_generic(const Epilogue& e, const float4 (&a)[8], const EpiRowCtx& c) {
-  const EpiCols ec = load_epi_cols(e, c.col);
-  const bool has_res = e.resid != nullptr, has_pos = e.pos != nullptr;
+__device__ __noinline__ void epi_rows_generic(const Epilogue& e, const Frag& f, const EpiRowCtx& c, int lane) {
+  const int tr = lane >> 2, tc2 = 2 * (lane & 3);
 #pragma unroll 1
-  for (int i = 0; i < 8; ++i) {
-    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), pv = qv;
-    if (has_res) qv = *reinterpret_cast<const float4*>(e.resid + (size_t)(c.res_row0 + c.prow + 4 * i) * e.ldr + c.col);
-    if (has_pos) pv = __ldg(reinterpret_cast<const float4*>(e.pos + (size_t)(c.pos_row0 + c.prow + 4 * i) * c.N + c.col));
-    float v[4];
-    apply_epi4(ec, a[i], has_pos, pv, has_res, qv, v);
-    store_tc_out4(e, c.orow0 + c.prow + 4 * i, c.col + c.ocol_add, v);
+  for (int ij = 0; ij < 16; ++ij) {
+    const int i = ij >> 2, j = ij & 3;
+    const uint32_t* r = (i < 2) ? f.a : f.b;
+    const int o = 4 * j + 2 * (i & 1);
+    const int col = c.col0 + 8 * j + tc2, rr = tr + 8 * i;
+    float v[2] = {__uint_as_float(r[o]), __uint_as_float(r[o + 1])};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float x = v[k];
+      if (e.bias) x += __ldg(e.bias + col + k);
+      if (e.scale) x = x * __ldg(e.scale + col + k) + __ldg(e.shift + col + k);
+      if (e.act == ACT_RELU) x = fmaxf(x, 0.f);
+      else if (e.act == ACT_GELU) x = gelu_tanh_fast(x);
+      else if (e.act == ACT_GELU_EXACT) x = gelu_tanh(x);
+      else if (e.act == ACT_SIGMOID) x = sigmoidf_(x);
+      if (e.pos) x += __ldg(e.pos + (size_t)(c.pos_row0 + rr) * c.N + col + k);
+      if (e.gate) x *= __ldg(e.gate + col + k);
+      if (e.resid) x += e.resid[(size_t)(c.res_row0 + rr) * e.ldr + col + k];
+      v[k] = x;
+    }
+    const int orow = c.orow0 + rr, ocol = col + c.ocol_add;
+    if (e.out) *reinterpret_cast<float2*>(e.out + (size_t)orow * e.ldc + ocol) = make_float2(v[0], v[1]);
+    if (e.out_bf16) {
+      const size_t off = (size_t)orow * e.ldc_bf16 + ocol;
+      if (e.out_lo) {
+        uint32_t hi, lo;
+        split_bf16x2(v[0], v[1], hi, lo);
+        *reinterpret_cast<uint32_t*>(e.out_bf16 + off) = hi;
+        *reinterpret_cast<uint32_t*>(e.out_lo + off) = lo;
+      } else {
+        *reinterpret_cast<uint32_t*>(e.out_bf16 + off) = e.out_f16 ? pack_f16x2(v[0], v[1]) : pack_bf16x2(v[0], v[1]);
+      }
+    }
   }
 }
 
@@ -198,8 +293,11 @@ static int classify_epilogue(const Epilogue& e) {
   if (e.gate) f |= EF_GATE;
   if (e.pos) f |= EF_POS;
   if (e.resid) f |= EF_RES;
+  if (e.ln_stats) f |= EF_LN;
   int o;
-  if (e.out && !e.out_bf16) o = EO_F32;
+  if (e.out && e.out_bf16 && e.stats_out && !e.out_f16) o = EO_F32X;
+  else if (e.stats_out) return EPI_GENERIC;                   // (rejected by the dispatcher: statistics need the compiled body)
+  else if (e.out && !e.out_bf16) o = EO_F32;
   else if (!e.out && e.out_bf16) o = e.out_lo ? EO_PAIR : (e.out_f16 ? EO_F16 : EO_BF16);
   else return EPI_GENERIC;
   const int k = epi_key(f, o);
@@ -210,10 +308,23 @@ static int classify_epilogue(const Epilogue& e) {
     case epi_key(EF_GELU, EO_BF16): case epi_key(EF_GELUX, EO_PAIR):
     case epi_key(EF_SCALE | EF_FLOOR, EO_BF16): case epi_key(EF_SCALE | EF_FLOOR, EO_PAIR): case epi_key(EF_SCALE | EF_FLOOR | EF_RES, EO_F32):
     case epi_key(EF_FLOOR, EO_BF16): case epi_key(EF_FLOOR, EO_PAIR):
+    case epi_key(EF_LN, EO_F16): case epi_key(EF_LN, EO_BF16):
+    case epi_key(EF_LN | EF_SCALE | EF_FLOOR, EO_PAIR): case epi_key(EF_LN | EF_SCALE | EF_FLOOR, EO_BF16):
+    case epi_key(EF_RES, EO_F32X): case epi_key(EF_SCALE | EF_FLOOR | EF_RES, EO_F32X):
       return k;
     default:
       return EPI_GENERIC;
   }
+}
+
+// 16 TMEM lanes x 32 fp32 columns, mma-fragment layout (see Frag)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 
 struct PairUnit { int m0, n0, kb0, kb1; };
@@ -225,6 +336,99 @@ __device__ __forceinline__ PairUnit decode_unit(const PairParams& p, int u, int 
   return q;
 }
 
+// The epilogue warps' loop over the units of their pair (F < 0: generic run-time-option body).
+template <int BN, int F, int O>
+__device__ __forceinline__ void epilogue_loop(const PairParams& p, const Epilogue& e, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
+                                              int warp, int lane, uint32_t rank, int pair, int nkb) {
+  constexpr int FF = F < 0 ? 0 : F;
+  const int quarter = warp & 3, half = (warp - PP_EPI_WARP0) >> 2;
+  const uint32_t lead_acc_empty0 = mapa(smem_u32(&acc_empty[0]), 0);
+  constexpr int NCH = BN / 64;                               // 32-column chunks per warp and unit
+  int it = 0;
+  for (int u = pair; u < p.units; u += p.npairs, ++it) {
+    const PairUnit q = decode_unit(p, u, nkb, BN);
+    const int buf = it & 1;
+    const int rbase = q.m0 + (int)rank * PBM + quarter * 32;  // first global row of this warp
+    // row bookkeeping once per unit (the 32 rows of a warp never straddle a residual / pos-embed / stream boundary: the host checks
+    // that those periods are multiples of 128), so the per-row work is address increments only
+    EpiRowCtx rc;
+    rc.res_row0 = e.resid_mod ? rbase % e.resid_mod : rbase;
+    rc.pos_row0 = e.pos_rows ? rbase % e.pos_rows : 0;
+    rc.orow0 = rbase; rc.ocol_add = 0; rc.N = p.N;
+    if (e.group_rows) { rc.orow0 = rbase % e.group_rows; rc.ocol_add = (rbase / e.group_rows) * e.group_col_stride; }
+    rc.col0 = q.n0 + half * (BN / 2);
+    EpiLoads<FF> cur, nxt;
+    if (F >= 0) epi_load<FF>(e, rc, lane, cur);               // first chunk's operands: in flight while the main loop still runs
+    LnRows ln;
+    if (FF & EF_LN) {
+      // fused LayerNorm: lane r sums the partial (sum, sum of squares) of row rbase + r in chunk order (deterministic), then every
+      // thread fetches the mean / rstd of its four rows
+      const float4* sp = reinterpret_cast<const float4*>(e.ln_stats + (size_t)(rbase + lane) * e.ln_chunks * 2);
+      float s1 = 0.f, s2 = 0.f;
+      for (int k = 0; k < (e.ln_chunks >> 1); ++k) { const float4 t = __ldg(sp + k); s1 += t.x; s2 += t.y; s1 += t.z; s2 += t.w; }
+      const float inv_c = 1.0f / (float)(e.ln_chunks * 32);
+      const float mean = s1 * inv_c;
+      const float rstd = rsqrtf(fmaxf(s2 * inv_c - mean * mean, 0.f) + e.ln_eps);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ln.m[i] = __shfl_sync(0xffffffffu, mean, (lane >> 2) + 8 * i);
+        ln.rs[i] = __shfl_sync(0xffffffffu, rstd, (lane >> 2) + 8 * i);
+      }
+    }
+    mbar_wait(&acc_full[buf], (it >> 1) & 1);
+    if (warp == PP_EPI_WARP0 && lane == 0 && it < 2) PTRACE(4 + 5 * it);          // accumulator complete
+    fence_after_sync();
+    const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (BN / 2));
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      rc.col0 = q.n0 + half * (BN / 2) + ch * 32;
+      Frag f;
+      tmem_ld_16x256b_x4(tacc + (uint32_t)(ch * 32), f.a);
+      tmem_ld_16x256b_x4(tacc + (16u << 16) + (uint32_t)(ch * 32), f.b);
+      if (F >= 0 && ch + 1 < NCH) {                           // next chunk's operands
+        EpiRowCtx rn = rc; rn.col0 = rc.col0 + 32;
+        epi_load<FF>(e, rn, lane, nxt);
+      }
+      tmem_ld_wait();
+      if (warp == PP_EPI_WARP0 && lane == 0 && it == 0 && ch == 0) PTRACE(7);
+      if (ch == NCH - 1) {                                    // accumulator fully copied out: hand the buffer back to the MMA warp
+        if (warp == PP_EPI_WARP0 && lane == 0 && it < 2) PTRACE(5 + 5 * it);      // TMEM drained
+        fence_before_sync();
+        __syncwarp();
+        // (nobody waits for the buffers of a pair's last two units)
+        if (lane == 0 && u + 2 * p.npairs < p.units) mbar_arrive_cluster(lead_acc_empty0 + (uint32_t)buf * 8u);
+      }
+      if (e.vt_out && rc.col0 >= e.vt_col0) {
+        // transposed V^T [sample][column][token] (bias-only epilogue, host check): per column the 8 threads of equal t%4 write 8
+        // consecutive tokens (16 bytes)
+        const int tr = lane >> 2, tc2 = 2 * (lane & 3);
+        uint16_t* vt = reinterpret_cast<uint16_t*>(e.vt_out);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = rc.col0 + 8 * j + tc2;
+          const float2 b2 = e.bias ? __ldg(reinterpret_cast<const float2*>(e.bias + col)) : make_float2(0.f, 0.f);
+          float2 c2 = make_float2(0.f, 0.f);
+          if (FF & EF_LN) c2 = __ldg(reinterpret_cast<const float2*>(e.ln_colsum + col));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = rbase + tr + 8 * i;
+            float2 a = frag_val(f, i, j);
+            if (FF & EF_LN) { a.x = ln.rs[i] * (a.x - ln.m[i] * c2.x); a.y = ln.rs[i] * (a.y - ln.m[i] * c2.y); }
+            uint16_t* o = vt + ((size_t)(row >> 10) * (p.N - e.vt_col0) + (col - e.vt_col0)) * 1024 + (row & 1023);
+            o[0] = cvt16(a.x + b2.x, e.out_f16);
+            o[1024] = cvt16(a.y + b2.y, e.out_f16);
+          }
+        }
+      }
+      if (F >= 0) epi_rows<FF, O>(e, f, rc, lane, cur, ln);
+      else epi_rows_generic(e, f, rc, lane);
+      if (warp == PP_EPI_WARP0 && lane == 0 && it == 0 && ch == 0) PTRACE(11);
+      if (F >= 0 && ch + 1 < NCH) cur = nxt;
+    }
+    if (warp == PP_EPI_WARP0 && lane == 0 && it < 2) PTRACE(6 + 5 * it);          // epilogue of the unit done (this warp)
+  }
+}
+
 template <int BN, bool X3, bool CONV>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmB,
@@ -233,8 +437,7 @@ k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int ST = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* staging = reinterpret_cast<float*>(smem + Cfg::RING_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES + Cfg::STAGING_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES);
   uint64_t* empty = full + ST;
   uint64_t* acc_full = empty + ST;        // 2
   uint64_t* acc_empty = acc_full + 2;     // 2 (the leader's are used)
@@ -262,191 +465,127 @@ k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) PTRACE(1);                           // prologue done (the dependency wait follows per role)
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer (both CTAs): own 128 A rows, own half of the W tile; the bytes of both CTAs are counted on the LEADER's full
-      // barrier, which only the leader arrives on (expect_tx of both CTAs' bytes): a follower-side arrive per k-block would put a
-      // cluster-scope fence on the producer's critical path.  The follower refills a stage only after ITS empty barrier fired, i.e. after
-      // the previous phase of the leader's full barrier completed, so bytes never land in the wrong phase.
-      // The W tiles do not depend on the previous kernel: the first ring-full of them is requested BEFORE griddepcontrol.wait, so that
-      // under programmatic dependent launch the weight fetch (HBM: a step streams more weights than the L2 holds) overlaps the
-      // predecessor's tail; the A tiles follow after the wait.
-      uint32_t g = 0;
-      const int cblocks = CONV ? p.conv_cin / 64 : 1;
-      bool waited_pdl = false;
-      for (int u = pair; u < p.units; u += p.npairs) {
-        const PairUnit q = decode_unit(p, u, nkb, BN);
-        const int m0 = q.m0 + (int)rank * PBM, nb = q.n0 + (int)rank * (BN / 2);
-        int cn = 0, cy = 0, cx = 0;
-        if (CONV) {
-          const int hw = p.conv_h * p.conv_w;
-          cn = m0 / hw; const int rem = m0 - cn * hw; cy = rem / p.conv_w; cx = rem - cy * p.conv_w;   // 128 consecutive pixels of one image row
-        }
-        auto load_b = [&](int kb, uint32_t gg) {
-          const int s = gg % ST;
-          uint8_t* a = smem + s * Cfg::STAGE_BYTES;
-          const uint32_t lead_full = mapa(smem_u32(&full[s]), 0);
-          if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);        // both CTAs' loads of this stage
-#pragma unroll
-          for (int o = 0; o < Cfg::NOP; ++o) tma_load_2d_pair(a + Cfg::B_OFF + o * Cfg::B_BYTES, o ? &tmBl : &tmB, lead_full, kb * PBK, nb);
-        };
-        auto load_a = [&](int kb, uint32_t gg) {
-          const int s = gg % ST;
-          uint8_t* a = smem + s * Cfg::STAGE_BYTES;
-          const uint32_t lead_full = mapa(smem_u32(&full[s]), 0);
-#pragma unroll
-          for (int o = 0; o < Cfg::NOP; ++o) {
-            if (CONV) {
-              const int tap = kb / cblocks, cb = kb - tap * cblocks;
-              tma_load_4d_pair(a + o * Cfg::A_BYTES, o ? &tmAl : &tmA, lead_full, cb * 64, cx + tap % 3 - 1, cy + tap / 3 - 1, cn);
-            } else {
-              tma_load_2d_pair(a + o * Cfg::A_BYTES, o ? &tmAl : &tmA, lead_full, kb * PBK, m0);
-            }
-          }
-        };
-        int kb = q.kb0;
-        if (!waited_pdl) {                                     // first unit: W tiles of the first ring-full ahead of the dependency wait
-          const int npre = (q.kb1 - q.kb0) < ST ? (q.kb1 - q.kb0) : ST;
-          for (int i = 0; i < npre; ++i) load_b(q.kb0 + i, g + i);
-          pdl_wait();
-          waited_pdl = true;
-          for (int i = 0; i < npre; ++i) load_a(q.kb0 + i, g + i);
-          kb += npre; g += npre;
-        }
-        for (; kb < q.kb1; ++kb, ++g) {
-          mbar_wait(&empty[g % ST], ((g / ST) & 1) ^ 1);
-          load_b(kb, g);
-          load_a(kb, g);
-        }
-      }
-      if (!waited_pdl) pdl_wait();
-    } else {
-      pdl_wait();
-    }
-    __syncwarp();
-  } else if (warp == 1) {
+  // (each role's code is dominated by its own setmaxnreg, so that ptxas applies the right register budget to it)
+  if (warp >= PP_EPI_WARP0) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PP_REGS_EPI));
+    // ===== epilogue warps (both CTAs): TMEM lane quarter = warp % 4, column half = (warp - 4) / 4
     pdl_wait();
-    if (rank == 0 && lane == 0) {
-      // ===== MMA issuer (leader only): UMMA M = 256 across the pair, accumulator buffer = unit parity
-      constexpr uint32_t idesc = make_idesc_bf16(2 * PBM, BN);
-      uint32_t g = 0;
-      int it = 0;
-      for (int u = pair; u < p.units; u += p.npairs, ++it) {
-        const PairUnit q = decode_unit(p, u, nkb, BN);
-        const int buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);       // both CTAs' epilogue warps have drained this accumulator
-        fence_after_sync();
-        const uint32_t tacc = tmem_base + buf * BN;
-        for (int kb = q.kb0; kb < q.kb1; ++kb, ++g) {
-          const int s = g % ST;
-          mbar_wait(&full[s], (g / ST) & 1);
-          if (kb == q.kb0) if (it < 2) PTRACE(2 + 5 * it);                // first stage of the unit landed
-          if (kb == q.kb1 - 1) if (it < 2) PTRACE(3 + 5 * it);            // last stage landed
-          fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES), b_addr = a_addr + Cfg::B_OFF;
-#pragma unroll
-          for (int k = 0; k < PBK / 16; ++k) {
-            const uint64_t ah = make_desc_k_sw128(a_addr + k * 32), bh = make_desc_k_sw128(b_addr + k * 32);
-            mma_f16_ss_pair(tacc, ah, bh, idesc, (kb > q.kb0 || k > 0) ? 1u : 0u);
-            if (X3) {
-              mma_f16_ss_pair(tacc, make_desc_k_sw128(a_addr + Cfg::A_BYTES + k * 32), bh, idesc, 1u);     // lo * hi
-              mma_f16_ss_pair(tacc, ah, make_desc_k_sw128(b_addr + Cfg::B_BYTES + k * 32), idesc, 1u);     // hi * lo
-            }
-          }
-          mma_commit_pair(&empty[s]);                          // frees stage s in both CTAs
-        }
-        mma_commit_pair(&acc_full[buf]);                       // the accumulators of both CTAs are complete
-      }
+#define DVD_EPI_CASE(F, O) case epi_key(F, O): epilogue_loop<BN, F, O>(p, e, tmem_base, acc_full, acc_empty, warp, lane, rank, pair, nkb); break;
+    switch (p.epi) {
+      DVD_EPI_CASE(0, EO_F32) DVD_EPI_CASE(0, EO_BF16) DVD_EPI_CASE(0, EO_PAIR) DVD_EPI_CASE(0, EO_F16)
+      DVD_EPI_CASE(EF_POS, EO_BF16) DVD_EPI_CASE(EF_POS, EO_PAIR)
+      DVD_EPI_CASE(EF_RES, EO_F32) DVD_EPI_CASE(EF_GATE | EF_RES, EO_F32)
+      DVD_EPI_CASE(EF_GELU, EO_BF16) DVD_EPI_CASE(EF_GELUX, EO_PAIR)
+      DVD_EPI_CASE(EF_SCALE | EF_FLOOR, EO_BF16) DVD_EPI_CASE(EF_SCALE | EF_FLOOR, EO_PAIR) DVD_EPI_CASE(EF_SCALE | EF_FLOOR | EF_RES, EO_F32)
+      DVD_EPI_CASE(EF_FLOOR, EO_BF16) DVD_EPI_CASE(EF_FLOOR, EO_PAIR)
+      DVD_EPI_CASE(EF_LN, EO_F16) DVD_EPI_CASE(EF_LN, EO_BF16)
+      DVD_EPI_CASE(EF_LN | EF_SCALE | EF_FLOOR, EO_PAIR) DVD_EPI_CASE(EF_LN | EF_SCALE | EF_FLOOR, EO_BF16)
+      DVD_EPI_CASE(EF_RES, EO_F32X) DVD_EPI_CASE(EF_SCALE | EF_FLOOR | EF_RES, EO_F32X)
+      default: epilogue_loop<BN, -1, 0>(p, e, tmem_base, acc_full, acc_empty, warp, lane, rank, pair, nkb); break;
     }
-    __syncwarp();
-  } else {
-    // ===== epilogue warps (both CTAs): TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
-    pdl_wait();
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
-    float* stage = staging + (warp - 2) * (32 * 32);
-    const uint32_t lead_acc_empty0 = mapa(smem_u32(&acc_empty[0]), 0);
-    const int prow = lane >> 3, pc = lane & 7;                 // phase 2: 4 rows x 8 column quads per warp instruction
-    constexpr int NCH = BN / 64;                               // 32-column chunks per warp and unit
-    int it = 0;
-    for (int u = pair; u < p.units; u += p.npairs, ++it) {
-      const PairUnit q = decode_unit(p, u, nkb, BN);
-      const int buf = it & 1;
-      const int rbase = q.m0 + (int)rank * PBM + quarter * 32;  // first global row of this warp
-      const int res_row0 = e.resid_mod ? rbase % e.resid_mod : rbase;
-      const int pos_row0 = e.pos_rows ? rbase % e.pos_rows : 0;
-      int orow0 = rbase, ocol_add = 0;
-      if (e.group_rows) { orow0 = rbase % e.group_rows; ocol_add = (rbase / e.group_rows) * e.group_col_stride; }
-      mbar_wait(&acc_full[buf], (it >> 1) & 1);
-      if (warp == 2 && lane == 0 && it < 2) PTRACE(4 + 5 * it);          // accumulator complete
-      fence_after_sync();
-      const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (BN / 2));
-#pragma unroll 1
-      for (int ch = 0; ch < NCH; ++ch) {
-        const int col0 = q.n0 + half * (BN / 2) + ch * 32;
-        // ---- phase 1 (thread = row = TMEM lane): TMEM -> registers -> swizzled staging (+ transposed V^T store, coalesced in this mapping)
-        uint32_t r[32];
-        tmem_ld_32x32(tacc + (uint32_t)(ch * 32), r);
-        tmem_ld_wait();
-        ETRACE(7);
-        if (ch == NCH - 1) {                                    // accumulator fully copied out: hand the buffer back to the MMA warp
-          if (warp == 2 && lane == 0 && it < 2) PTRACE(5 + 5 * it);      // TMEM drained
-          fence_before_sync();
-          __syncwarp();
-          // (nobody waits for the buffers of a pair's last two units)
-          if (lane == 0 && u + 2 * p.npairs < p.units) mbar_arrive_cluster(lead_acc_empty0 + (uint32_t)buf * 8u);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        if (e.vt_out && col0 >= e.vt_col0) {                    // bias-only epilogue (host check)
-          float bv[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
-          }
-          const int row_t = rbase + lane;
-          uint16_t* o = reinterpret_cast<uint16_t*>(e.vt_out) + ((size_t)(row_t >> 10) * (p.N - e.vt_col0) + (col0 - e.vt_col0)) * 1024 + (row_t & 1023);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[(size_t)j * 1024] = cvt16(__uint_as_float(r[j]) + bv[j], e.out_f16);
-        }
-        __syncwarp();
-        ETRACE(8);
-        // ---- phase 2 (8 lanes = one 128-byte row segment): staging -> fused epilogue -> global
-        const int col = col0 + 4 * pc;
-        float4 a[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + prow;
-          a[i] = *reinterpret_cast<const float4*>(stage + rr * 32 + ((pc ^ (rr & 7)) << 2));
-        }
-        ETRACE(9);
-        {
-          // Row bookkeeping happens once per unit (rows of a 32-row group never straddle a residual / pos-embed / stream boundary: the
-          // host checks that those periods are multiples of 128), so the per-row work is address increments only.
-          const EpiRowCtx rc{col, prow, res_row0, pos_row0, orow0, ocol_add, p.N};
-          ETRACE(10);
-#define DVD_EPI_CASE(F, O) case epi_key(F, O): epi_rows<F, O>(e, a, rc); break;
-          switch (p.epi) {
-            DVD_EPI_CASE(0, EO_F32) DVD_EPI_CASE(0, EO_BF16) DVD_EPI_CASE(0, EO_PAIR) DVD_EPI_CASE(0, EO_F16)
-            DVD_EPI_CASE(EF_POS, EO_BF16) DVD_EPI_CASE(EF_POS, EO_PAIR)
-            DVD_EPI_CASE(EF_RES, EO_F32) DVD_EPI_CASE(EF_GATE | EF_RES, EO_F32)
-            DVD_EPI_CASE(EF_GELU, EO_BF16) DVD_EPI_CASE(EF_GELUX, EO_PAIR)
-            DVD_EPI_CASE(EF_SCALE | EF_FLOOR, EO_BF16) DVD_EPI_CASE(EF_SCALE | EF_FLOOR, EO_PAIR) DVD_EPI_CASE(EF_SCALE | EF_FLOOR | EF_RES, EO_F32)
-            DVD_EPI_CASE(EF_FLOOR, EO_BF16) DVD_EPI_CASE(EF_FLOOR, EO_PAIR)
-            default: epi_rows_generic(e, a, rc); break;
-          }
 #undef DVD_EPI_CASE
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PP_REGS_CTRL));
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===== TMA producer (both CTAs): own 128 A rows, own half of the W tile; the bytes of both CTAs are counted on the LEADER's full
+        // barrier, which only the leader arrives on (expect_tx of both CTAs' bytes): a follower-side arrive per k-block would put a
+        // cluster-scope fence on the producer's critical path.  The follower refills a stage only after ITS empty barrier fired, i.e. after
+        // the previous phase of the leader's full barrier completed, so bytes never land in the wrong phase.
+        // The W tiles do not depend on the previous kernel: the first ring-full of them is requested BEFORE griddepcontrol.wait, so that
+        // under programmatic dependent launch the weight fetch (HBM: a step streams more weights than the L2 holds) overlaps the
+        // predecessor's tail; the A tiles follow after the wait.
+        uint32_t g = 0;
+        const int cblocks = CONV ? p.conv_cin / 64 : 1;
+        bool waited_pdl = false;
+        for (int u = pair; u < p.units; u += p.npairs) {
+          const PairUnit q = decode_unit(p, u, nkb, BN);
+          const int m0 = q.m0 + (int)rank * PBM, nb = q.n0 + (int)rank * (BN / 2);
+          int cn = 0, cy = 0, cx = 0;
+          if (CONV) {
+            const int hw = p.conv_h * p.conv_w;
+            cn = m0 / hw; const int rem = m0 - cn * hw; cy = rem / p.conv_w; cx = rem - cy * p.conv_w;   // 128 consecutive pixels of one image row
+          }
+          auto load_b = [&](int kb, uint32_t gg) {
+            const int s = gg % ST;
+            uint8_t* a = smem + s * Cfg::STAGE_BYTES;
+            const uint32_t lead_full = mapa(smem_u32(&full[s]), 0);
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);        // both CTAs' loads of this stage
+  #pragma unroll
+            for (int o = 0; o < Cfg::NOP; ++o) tma_load_2d_pair(a + Cfg::B_OFF + o * Cfg::B_BYTES, o ? &tmBl : &tmB, lead_full, kb * PBK, nb);
+          };
+          auto load_a = [&](int kb, uint32_t gg) {
+            const int s = gg % ST;
+            uint8_t* a = smem + s * Cfg::STAGE_BYTES;
+            const uint32_t lead_full = mapa(smem_u32(&full[s]), 0);
+  #pragma unroll
+            for (int o = 0; o < Cfg::NOP; ++o) {
+              if (CONV) {
+                const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                tma_load_4d_pair(a + o * Cfg::A_BYTES, o ? &tmAl : &tmA, lead_full, cb * 64, cx + tap % 3 - 1, cy + tap / 3 - 1, cn);
+              } else {
+                tma_load_2d_pair(a + o * Cfg::A_BYTES, o ? &tmAl : &tmA, lead_full, kb * PBK, m0);
+              }
+            }
+          };
+          int kb = q.kb0;
+          if (!waited_pdl) {                                     // first unit: W tiles of the first ring-full ahead of the dependency wait
+            const int npre = (q.kb1 - q.kb0) < ST ? (q.kb1 - q.kb0) : ST;
+            for (int i = 0; i < npre; ++i) load_b(q.kb0 + i, g + i);
+            pdl_wait();
+            waited_pdl = true;
+            for (int i = 0; i < npre; ++i) load_a(q.kb0 + i, g + i);
+            kb += npre; g += npre;
+          }
+          for (; kb < q.kb1; ++kb, ++g) {
+            mbar_wait(&empty[g % ST], ((g / ST) & 1) ^ 1);
+            load_b(kb, g);
+            load_a(kb, g);
+          }
         }
-        ETRACE(11);
-        __syncwarp();                                           // the staging tile is rewritten by the next chunk
-        ETRACE(12);
+        if (!waited_pdl) pdl_wait();
+      } else {
+        pdl_wait();
       }
-      if (warp == 2 && lane == 0 && it < 2) PTRACE(6 + 5 * it);          // epilogue of the unit done (this warp)
+      __syncwarp();
+    } else if (warp == 1) {
+      pdl_wait();
+      if (rank == 0 && lane == 0) {
+        // ===== MMA issuer (leader only): UMMA M = 256 across the pair, accumulator buffer = unit parity
+        constexpr uint32_t idesc = make_idesc_bf16(2 * PBM, BN);
+        uint32_t g = 0;
+        int it = 0;
+        for (int u = pair; u < p.units; u += p.npairs, ++it) {
+          const PairUnit q = decode_unit(p, u, nkb, BN);
+          const int buf = it & 1;
+          mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);       // both CTAs' epilogue warps have drained this accumulator
+          fence_after_sync();
+          const uint32_t tacc = tmem_base + buf * BN;
+          for (int kb = q.kb0; kb < q.kb1; ++kb, ++g) {
+            const int s = g % ST;
+            mbar_wait(&full[s], (g / ST) & 1);
+            if (kb == q.kb0) if (it < 2) PTRACE(2 + 5 * it);                // first stage of the unit landed
+            if (kb == q.kb1 - 1) if (it < 2) PTRACE(3 + 5 * it);            // last stage landed
+            fence_after_sync();
+            const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES), b_addr = a_addr + Cfg::B_OFF;
+  #pragma unroll
+            for (int k = 0; k < PBK / 16; ++k) {
+              const uint64_t ah = make_desc_k_sw128(a_addr + k * 32), bh = make_desc_k_sw128(b_addr + k * 32);
+              mma_f16_ss_pair(tacc, ah, bh, idesc, (kb > q.kb0 || k > 0) ? 1u : 0u);
+              if (X3) {
+                mma_f16_ss_pair(tacc, make_desc_k_sw128(a_addr + Cfg::A_BYTES + k * 32), bh, idesc, 1u);     // lo * hi
+                mma_f16_ss_pair(tacc, ah, make_desc_k_sw128(b_addr + Cfg::B_BYTES + k * 32), idesc, 1u);     // hi * lo
+              }
+            }
+            mma_commit_pair(&empty[s]);                          // frees stage s in both CTAs
+          }
+          mma_commit_pair(&acc_full[buf]);                       // the accumulators of both CTAs are complete
+        }
+      }
+      __syncwarp();
     }
   }
-  if (threadIdx.x == 64) PTRACE(14);                          // this CTA's epilogue warps are done
+  if (threadIdx.x == 32 * PP_EPI_WARP0) PTRACE(14);                          // this CTA's epilogue warps are done
   fence_before_sync();
   cluster_sync_all();                                          // the peer's smem / TMEM must outlive every MMA that reads it
   if (warp == 1) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
@@ -574,6 +713,10 @@ int gemm_pair_dispatch(const TcMat& A, const TcMat& W, int M, int N, int K, cons
   const bool conv = conv_h > 0, x3 = A.lo != nullptr;
   DVD_REQUIRE(gemm_pair_supported(M, N, K, conv), "gemm_pair: unsupported shape M=%d N=%d K=%d", M, N, K);
   DVD_REQUIRE(epilogue_periods_ok(e), "gemm_pair: resid_mod / pos_rows / group_rows must be multiples of 128");
+  DVD_REQUIRE((!e.ln_stats && !e.stats_out) || classify_epilogue(e) != EPI_GENERIC, "gemm_pair: fused-LN / row-statistics epilogue combination not compiled");
+  DVD_REQUIRE(!e.ln_stats || (e.ln_colsum && e.ln_chunks > 0 && e.ln_chunks % 2 == 0 && (reinterpret_cast<uintptr_t>(e.ln_stats) & 15) == 0),
+              "gemm_pair: fused LN needs ln_colsum and an even number of 32-column chunks");
+  DVD_REQUIRE(!e.stats_out || (N % 32 == 0 && !e.group_rows), "gemm_pair: row statistics need N %% 32 == 0 and no stream remap");
   DVD_REQUIRE(!conv || (conv_w % 128 == 0 && conv_cin % 64 == 0 && K == 9 * conv_cin), "gemm_pair: bad conv geometry");
   const int bn = pick_bn(M, N, K, x3, sm_count() / 2);
   if (conv) return x3 ? launch_pair_bn<true, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st)

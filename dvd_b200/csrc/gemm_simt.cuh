@@ -39,6 +39,16 @@ struct Epilogue {
   //   vt_out[(row / 1024) * (N - vt_col0) + (col - vt_col0)][row % 1024]      i.e. V^T [sample, C_v, T = 1024]
   __nv_bfloat16* vt_out = nullptr;
   int vt_col0 = 0;
+  // tensor path (persistent pair kernel), LayerNorm fused into the CONSUMER GEMM: A holds the raw rows (16-bit operand), W is
+  // pre-multiplied by the LN gain, and the epilogue applies
+  //     v = rstd[row] * (acc - mean[row] * ln_colsum[col]) + bias[col]            (bias = W beta)
+  // before scale / activation / ...; mean and rstd come from per-row partial sums left by the PRODUCER of the rows:
+  const float* ln_stats = nullptr;    // [M][ln_chunks][2]: (sum, sum of squares) per 32-column chunk of the row
+  const float* ln_colsum = nullptr;   // [N] sum over k of the (rounded) pre-multiplied weights
+  int ln_chunks = 0;                  // chunks per row = C / 32
+  float ln_eps = 0.f;
+  // producer side: next to out (fp32) and out_bf16 (+ out_lo), emit the partial statistics of the OUTPUT rows
+  float* stats_out = nullptr;         // [M][N / 32][2]
 };
 
 __device__ __forceinline__ float apply_epilogue(const Epilogue& e, float v, int row, int col, int N) {

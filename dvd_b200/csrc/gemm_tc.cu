@@ -364,6 +364,7 @@ int gemm_tc(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue&
   int rc = check_epilogue(e, N); if (rc) return rc;
   const bool periods_ok = e.resid_mod % 128 == 0 && e.pos_rows % 128 == 0 && e.group_rows % 128 == 0;
   if (!use_v1() && periods_ok && gemm_pair_supported(M, N, K, false)) return gemm_pair_dispatch(A, W, M, N, K, e, 0, 0, 0, 0, st);
+  DVD_REQUIRE(!e.ln_stats && !e.stats_out, "gemm_tc: fused LayerNorm / row statistics need the CTA-pair kernel (M %% 256 == 0, N %% 64 == 0)");
   const bool x3 = A.lo != nullptr;
   // wide tiles only when they still fill the machine
   const bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) * 100 >= 190LL * sm_count());

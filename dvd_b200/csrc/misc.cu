@@ -534,6 +534,49 @@ int posenc_add(float* X, const float* hs, const float* ws, const float* hpe, con
   return 0;
 }
 
+// posenc_add for the fused-LayerNorm path: one warp per token row; also writes the row as the 16-bit operand of the next GEMM (bf16 or
+// pair) and its (sum, sum of squares) for the LayerNorm that GEMM's epilogue applies (slot 0 = whole row, the other chunk slots zero).
+__global__ void __launch_bounds__(256) k_posenc_ln(float* __restrict__ X, const float4* __restrict__ hs, const float4* __restrict__ ws,
+                                                   const float4* __restrict__ hpe, const float4* __restrict__ wpe, __nv_bfloat16* __restrict__ hi,
+                                                   __nv_bfloat16* __restrict__ lo, float* __restrict__ stats, int chunks, int rows) {
+  constexpr int C4 = 384;                       // 1536 / 4
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int tok = row & 1023, n = row >> 10;
+  float4* xr = reinterpret_cast<float4*>(X) + (size_t)row * C4;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int c = lane + 32 * i;
+    float4 x = xr[c];
+    const float4 a = __ldg(hs + (size_t)n * C4 + c), b = __ldg(ws + (size_t)n * C4 + c);
+    const float4 hp = __ldg(hpe + (size_t)(tok >> 5) * C4 + c), wp = __ldg(wpe + (size_t)(tok & 31) * C4 + c);
+    // CA:153: out = x + h_pos_encoding + w_pos_encoding (left to right)
+    x.x = (x.x + a.x * hp.x) + b.x * wp.x; x.y = (x.y + a.y * hp.y) + b.y * wp.y;
+    x.z = (x.z + a.z * hp.z) + b.z * wp.z; x.w = (x.w + a.w * hp.w) + b.w * wp.w;
+    xr[c] = x;
+    uint2 u, l;
+    split_bf16x2(x.x, x.y, u.x, l.x);
+    split_bf16x2(x.z, x.w, u.y, l.y);
+    *reinterpret_cast<uint2*>(hi + ((size_t)row * C4 + c) * 4) = u;
+    if (lo) *reinterpret_cast<uint2*>(lo + ((size_t)row * C4 + c) * 4) = l;
+    s1 += (x.x + x.y) + (x.z + x.w);
+    s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  float2* sr = reinterpret_cast<float2*>(stats) + (size_t)row * chunks;
+  for (int k = lane; k < chunks; k += 32) sr[k] = k == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+}
+int posenc_add_ln(float* X, const float* hs, const float* ws, const float* hpe, const float* wpe, int N, int C, __nv_bfloat16* x16,
+                  __nv_bfloat16* x16_lo, float* stats, int chunks, cudaStream_t st) {
+  DVD_REQUIRE(X && hs && ws && hpe && wpe && x16 && stats && C == 1536 && chunks == C / 32, "posenc_add_ln: bad args");
+  const int rows = N * 1024;
+  k_posenc_ln<<<cdiv(rows, 8), 256, 0, st>>>(X, (const float4*)hs, (const float4*)ws, (const float4*)hpe, (const float4*)wpe, x16, x16_lo, stats,
+                                             chunks, rows);
+  DVD_LAUNCH_CHECK("k_posenc_ln");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ depthwise 3x3
 __global__ void __launch_bounds__(256) k_dwconv(const float4* __restrict__ in, const float4* __restrict__ w9, const float4* __restrict__ sc,
                                                 const float4* __restrict__ sh, float* __restrict__ out, __nv_bfloat16* __restrict__ out16,

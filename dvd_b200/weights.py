@@ -89,6 +89,14 @@ class PackedWeights:
             m.bf16, m.bf16_lo = h.data_ptr(), l.data_ptr()
         return m
 
+    def _ln_fold(self, w64: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+        wp = (w64 * gamma.double()[None, :]).float()
+        m = self._mat(wp)
+        hi, lo = self.keep[-2], self.keep[-1]                      # the pair _mat just made
+        colsum = (hi.double() + lo.double()).sum(1).float()
+        cvec = (w64 @ beta.double()).float()
+        return m, self._vec(colsum), self._vec(cvec)
+
     def _bn(self, sd, prefix):
         w, b = sd[prefix + "bn.weight"].float(), sd[prefix + "bn.bias"].float()
         mu, var = sd[prefix + "bn.running_mean"].float(), sd[prefix + "bn.running_var"].float()
@@ -144,6 +152,13 @@ class PackedWeights:
             L.bn2_scale, L.bn2_shift = self._bn(sd, f + "depthwise_conv.")
             L.conv2 = self._mat(sd[f + "conv2.conv.weight"].reshape(1536, 2048))
             L.bn3_scale, L.bn3_shift = self._bn(sd, f + "conv2.")
+            if self.with_bf16:
+                # LayerNorm folded into the consumer GEMMs (fused-LN epilogue, csrc/gemm_pair.cu): W' = W * gamma, colsum of the ROUNDED
+                # pair, cvec = W beta (float64 sums)
+                wq = torch.cat([sd[p + "attn.linear_q.weight"], sd[p + "attn.linear_k.weight"], sd[p + "attn.linear_v.weight"]], 0).double()
+                L.qkv_ln, L.qkv_colsum, L.qkv_cvec = self._ln_fold(wq, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+                wc = sd[f + "conv1.conv.weight"].reshape(2048, 1536).double()
+                L.conv1_ln, L.conv1_colsum, L.conv1_cvec = self._ln_fold(wc, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
         T.dec_ln_w, T.dec_ln_b = self._vec(sd["decoder.layer_norm.weight"]), self._vec(sd["decoder.layer_norm.bias"])
         T.fin = self._mat(sd["final_layer2.linear.weight"], bf16=False); T.fin_b = self._vec(sd["final_layer2.linear.bias"])
         T.fin_ada = self._mat(sd["final_layer2.adaLN_modulation.1.weight"], bf16=False)

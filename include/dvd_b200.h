@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DVD_ABI_VERSION 2
+#define DVD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DVD_API __attribute__((visibility("default")))
@@ -68,6 +68,12 @@ typedef struct dvd_dec_layer {          /* CA:343-396 DecoderLayer, CA:13-57 fee
   const float *bn2_scale, *bn2_shift;
   dvd_mat_t conv2;                      /* [1536,2048]                                    */
   const float *bn3_scale, *bn3_shift;
+  /* LayerNorm folded into the consumer GEMM (DVD_PREC_BF16X3): W' = W * gamma (per input channel), colsum[n] = sum_k W'[n][k] of the
+   * ROUNDED pair, cvec = W beta.  The epilogue computes rstd * (x W'^T - mean * colsum) + cvec from the raw residual rows. */
+  dvd_mat_t qkv_ln;                     /* [4608,1536] = qkv * norm1.weight               */
+  const float *qkv_colsum, *qkv_cvec;   /* [4608]                                         */
+  dvd_mat_t conv1_ln;                   /* [2048,1536] = conv1 * norm2.weight             */
+  const float *conv1_colsum, *conv1_cvec;   /* [2048]                                     */
 } dvd_dec_layer_t;
 
 /* Packed weights of the live part of DiT-S/2 (tv=True): CM:361-459.  Blocks 0..10 are dead

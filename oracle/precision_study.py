@@ -128,5 +128,95 @@ def main():
         sys.stdout.flush()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--ln-fusion" not in sys.argv:
     main()
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm-fusion study
+# Would feeding the RAW residual stream (as a bf16 pair) to the consumer GEMM and applying the normalisation in its epilogue,
+#   LN(x) W^T = rstd * (x W'^T - mean * colsum(W')) + (beta W^T),   W' = W * gamma,
+# keep the accuracy?  The operand error is then relative to |x|, not to |x - mean| / std.
+def ln_linear_fused(x, w_ln, b_ln, eps, W, mode="x3", mod=None):
+    """x [..., C] raw; returns LN(x)(*w_ln + b_ln)[*(1+scale)+shift] @ W^T computed the fused way with operands rounded by `mode`."""
+    C = x.shape[-1]
+    mean = x.mean(-1, keepdim=True)
+    var = (x * x).mean(-1, keepdim=True) - mean * mean                # single-pass statistics (sum, sum of squares)
+    rstd = torch.rsqrt(var + eps)
+    g = torch.ones(C) if w_ln is None else w_ln
+    b = torch.zeros(C) if b_ln is None else b_ln
+    if mod is not None:                                               # adaLN: (LN*g + b) * (1 + scale) + shift, per sample
+        shift, scale = mod
+        outs = []
+        for n in range(x.shape[0]):
+            gg, bb = g * (1 + scale[n]), b * (1 + scale[n]) + shift[n]
+            Wp = W * gg[None, :]
+            acc = TF.linear(rnd(x[n], mode), rnd(Wp, mode))
+            outs.append(rstd[n] * (acc - mean[n] * Wp.sum(1)[None, :]) + (W @ bb)[None, :])
+        return torch.stack(outs)
+    Wp = W * g[None, :]
+    acc = TF.linear(rnd(x, mode), rnd(Wp, mode))
+    return rstd * (acc - mean * Wp.sum(1)) + (W @ b)
+
+
+def decoder_fused(sd, x, mode="x3"):
+    """oracle.decoder with LN1 -> q|k|v and LN2 -> conv1 computed the fused way (everything else as in the 'all x3' case)."""
+    N, C, H, W = x.shape
+    avg = x.mean(dim=(2, 3), keepdim=True)
+    pd = "decoder.position_dec."
+
+    def scale(hw):
+        h = TF.relu(TF.conv2d(avg, sd[pd + f"{hw}_scale.0.weight"], sd[pd + f"{hw}_scale.0.bias"]))
+        return torch.sigmoid(TF.conv2d(h, sd[pd + f"{hw}_scale.2.weight"], sd[pd + f"{hw}_scale.2.bias"]))
+    x = x + scale("h") * sd[pd + "h_position_encoder"][:, :, :H, :] + scale("w") * sd[pd + "w_position_encoder"][:, :, :, :W]
+    out = x.view(N, C, H * W).permute(0, 2, 1).contiguous()
+    lin = lambda a, w: TF.linear(rnd(a, mode), rnd(w, mode))
+    for i in range(6):
+        p = f"decoder.layer_stack.{i}."
+        Wqkv = torch.cat([sd[p + "attn.linear_q.weight"], sd[p + "attn.linear_k.weight"], sd[p + "attn.linear_v.weight"]], 0)
+        qkv = ln_linear_fused(out, sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5, Wqkv, mode)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        o = O._mha_core(q, k, v, O.HEADS, 1.0 / 16.0)
+        out = out + lin(o, sd[p + "attn.fc.weight"])
+        f = p + "feed_forward."
+        h = ln_linear_fused(out, sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5, sd[f + "conv1.conv.weight"].view(2048, C), mode)
+        h = h.transpose(1, 2).contiguous().view(N, 2048, H, W)
+        h = TF.relu(O._bn(sd, f + "conv1.", h))
+        h = TF.relu(O._bn(sd, f + "depthwise_conv.", TF.conv2d(h, sd[f + "depthwise_conv.conv.weight"], padding=1, groups=2048)))
+        h = TF.relu(O._bn(sd, f + "conv2.", TF.conv2d(rnd(h, mode), rnd(sd[f + "conv2.conv.weight"], mode))))
+        out = out + h.view(N, C, H * W).transpose(1, 2)
+    return O._ln(out, 1e-5, sd["decoder.layer_norm.weight"], sd["decoder.layer_norm.bias"])
+
+
+def ln_fusion_study():
+    torch.set_num_threads(8)
+    sd = synth.make_state_dict(1234, live_only=True)
+    inp = synth.make_doc_inputs(0, H=192, W=256)
+    inp.pop("photo")
+    patch()
+    ref = run(sd, inp, {})
+    groups = ["pyramid", "embed", "dit", "dit_attn", "decoder", "decoder_attn"]
+    x3 = {**{g: "x3" for g in groups}, "dit_attn": "fp16", "decoder_attn": "fp16"}
+    base = run(sd, inp, x3)
+    e = (base - ref).abs()
+    print(f"{'x3 + fp16 attention (shipping mode)':44s} mean {float(e.mean()):.3e} max {float(e.max()):.3e}  ({float(e.mean()) * 2015.5:.4f} px mean @4032)")
+    dec = O.decoder
+    O.decoder = lambda sd_, x: decoder_fused(sd_, x, "x3")
+    try:
+        out = run(sd, inp, x3)
+    finally:
+        O.decoder = dec
+    e = (out - ref).abs()
+    print(f"{'... with decoder LN1/LN2 fused into the GEMMs':44s} mean {float(e.mean()):.3e} max {float(e.max()):.3e}  ({float(e.mean()) * 2015.5:.4f} px mean @4032)")
+    # how far from zero-mean are the decoder's rows?
+    stats = []
+    O.decoder = lambda sd_, x: (stats.append(x), dec(sd_, x))[1]
+    try:
+        run(sd, inp, {})
+    finally:
+        O.decoder = dec
+    x = stats[0].flatten(2).transpose(1, 2)
+    print(f"decoder input rows: |mean| / std  median {float((x.mean(-1).abs() / x.std(-1)).median()):.3f}  max {float((x.mean(-1).abs() / x.std(-1)).max()):.3f}")
+
+
+if __name__ == "__main__" and "--ln-fusion" in sys.argv:
+    ln_fusion_study()
