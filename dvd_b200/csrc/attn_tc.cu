@@ -133,23 +133,24 @@ __global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __g
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer
+    {
+      // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (tc_common.cuh)
       constexpr uint32_t idesc_qk = F16 ? make_idesc_f16(AQ, AKV) : make_idesc_bf16(AQ, AKV);     // 128 x 64
       constexpr uint32_t idesc_pv = F16 ? make_idesc_f16(AQ, D) : make_idesc_bf16(AQ, D);         // 128 x D
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);                             // warp-uniform for the compiler
+      const uint64_t q_desc = make_desc_k_sw128(smem_u32(sQ)), p_desc = make_desc_k_sw128(smem_u32(sP));
       auto issue_qk = [&](int t) {
         const int s = t % ST, b = t % Cfg::NSB;
         mbar_wait(&k_full[s], (t / ST) & 1);
         mbar_wait(&s_empty[b], ((t / Cfg::NSB) & 1) ^ 1);
         fence_after_sync();
-        const uint32_t k_addr = smem_u32(sKV + s * Cfg::STAGE_BYTES);
+        const uint64_t k_desc = make_desc_k_sw128(smem_u32(sKV + s * Cfg::STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          mma_f16_ss(tmem_base + b * AKV, make_desc_k_sw128(q_addr + (k >> 2) * (AQ * 128) + (k & 3) * 32),
-                     make_desc_k_sw128(k_addr + (k >> 2) * (AKV * 128) + (k & 3) * 32), idesc_qk, k ? 1u : 0u);
-        mma_commit(&s_full[b]);
-        mma_commit(&k_empty[s]);                                  // K stage free as soon as QK^T(t) has read it
+        for (int k = 0; k < D / 16; ++k)                          // descriptor start field: 16-byte units
+          mma_ss_elect(tbase + b * AKV, q_desc + (uint64_t)(((k >> 2) * (AQ * 128) + (k & 3) * 32) >> 4),
+                       k_desc + (uint64_t)(((k >> 2) * (AKV * 128) + (k & 3) * 32) >> 4), idesc_qk, k ? 1u : 0u);
+        mma_commit_elect(&s_full[b]);
+        mma_commit_elect(&k_empty[s]);                            // K stage free as soon as QK^T(t) has read it
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
@@ -158,13 +159,12 @@ __global__ void __launch_bounds__(ATHREADS, D == 64 ? 3 : 1) k_attn_tc(const __g
         mbar_wait(&v_full[t % ST], (t / ST) & 1);
         mbar_wait(p_full, t & 1);
         fence_after_sync();
-        const uint32_t v_addr = smem_u32(sKV + (t % ST) * Cfg::STAGE_BYTES + Cfg::K_BYTES);
+        const uint64_t v_desc = make_desc_k_sw128(smem_u32(sKV + (t % ST) * Cfg::STAGE_BYTES + Cfg::K_BYTES));
 #pragma unroll
         for (int k = 0; k < AKV / 16; ++k)
-          mma_f16_ss(tmem_base + Cfg::O_COL, make_desc_k_sw128(p_addr + k * 32), make_desc_k_sw128(v_addr + k * 32), idesc_pv,
-                     (t | k) ? 1u : 0u);
-        mma_commit(&v_empty[t % ST]);                             // V^T stage free
-        mma_commit(pv_done);                                      // P buffer free, O(t) complete
+          mma_ss_elect(tbase + Cfg::O_COL, p_desc + (uint64_t)(k * 2), v_desc + (uint64_t)(k * 2), idesc_pv, (t | k) ? 1u : 0u);
+        mma_commit_elect(&v_empty[t % ST]);                       // V^T stage free
+        mma_commit_elect(pv_done);                                // P buffer free, O(t) complete
       }
     }
     __syncwarp();
@@ -327,6 +327,7 @@ int attention_tc_multi(const void* q, int ldq, const void* const* k, int ldk, co
 int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* vt, __nv_bfloat16* o, __nv_bfloat16* o_lo, int ldo, int nsamp,
                  int heads, int T, int d, float scale, int kv_div, int f16, cudaStream_t st) {
   DVD_REQUIRE(q && k && vt && o, "attention_tc: null pointer");
+  if (attention_pair_supported(T, d, 1)) return attention_pair(q, ldq, k, ldk, vt, o, o_lo, ldo, nsamp, heads, T, scale, kv_div, f16, st);
   __nv_bfloat16* const* olo = o_lo ? &o_lo : nullptr;
   return attention_tc_multi(q, ldq, &k, ldk, &vt, &o, olo, ldo, &kv_div, 1, nsamp, heads, T, d, scale, f16, st);
 }

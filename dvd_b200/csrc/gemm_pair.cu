@@ -62,51 +62,6 @@ struct PairParams {
   int epi;                        // epi_key(flags, out) of a compiled epilogue body, or EPI_GENERIC
 };
 
-// ---- cluster / pair PTX helpers
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-// arrive on a barrier of (possibly) the other CTA of the pair.  Default semantics (.release.cta): the orderings that matter here are
-// carried by tcgen05.fence / TMA complete_tx, and a .release.cluster arrive costs a MEMBAR.ALL.GPU (~0.7 us, measured) every time.
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA loads of a CTA pair: the data lands in THIS CTA's smem, the transaction bytes are counted on the barrier at `bar_cluster_addr`
-__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive (once all previously issued MMAs have completed) on the barrier at the same smem offset in BOTH CTAs of the pair
-__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-
 // ---- optional phase trace (-DDVD_GEMM_TRACE, tools/gemm_trace.py): %globaltimer per CTA at the phase boundaries of its first two units
 #ifdef DVD_GEMM_TRACE
 __device__ unsigned long long g_pair_trace[512][16];
@@ -550,9 +505,11 @@ k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       __syncwarp();
     } else if (warp == 1) {
       pdl_wait();
-      if (rank == 0 && lane == 0) {
-        // ===== MMA issuer (leader only): UMMA M = 256 across the pair, accumulator buffer = unit parity
+      if (rank == 0) {
+        // ===== MMA issuer (leader only): UMMA M = 256 across the pair, accumulator buffer = unit parity.  The whole warp runs the loop
+        // and one elected lane issues (tc_common.cuh: inside an `if (lane == 0)` region every UMMA costs an elect / branch loop).
         constexpr uint32_t idesc = make_idesc_bf16(2 * PBM, BN);
+        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);       // warp-uniform for the compiler
         uint32_t g = 0;
         int it = 0;
         for (int u = pair; u < p.units; u += p.npairs, ++it) {
@@ -560,26 +517,29 @@ k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int buf = it & 1;
           mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);       // both CTAs' epilogue warps have drained this accumulator
           fence_after_sync();
-          const uint32_t tacc = tmem_base + buf * BN;
+          const uint32_t tacc = tbase + buf * BN;
           for (int kb = q.kb0; kb < q.kb1; ++kb, ++g) {
             const int s = g % ST;
             mbar_wait(&full[s], (g / ST) & 1);
-            if (kb == q.kb0) if (it < 2) PTRACE(2 + 5 * it);                // first stage of the unit landed
-            if (kb == q.kb1 - 1) if (it < 2) PTRACE(3 + 5 * it);            // last stage landed
+            if (lane == 0) {
+              if (kb == q.kb0) if (it < 2) PTRACE(2 + 5 * it);              // first stage of the unit landed
+              if (kb == q.kb1 - 1) if (it < 2) PTRACE(3 + 5 * it);          // last stage landed
+            }
             fence_after_sync();
-            const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES), b_addr = a_addr + Cfg::B_OFF;
+            const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+            const uint64_t ad = make_desc_k_sw128(a_addr), bd = make_desc_k_sw128(a_addr + Cfg::B_OFF);   // start field: 16-byte units
   #pragma unroll
             for (int k = 0; k < PBK / 16; ++k) {
-              const uint64_t ah = make_desc_k_sw128(a_addr + k * 32), bh = make_desc_k_sw128(b_addr + k * 32);
-              mma_f16_ss_pair(tacc, ah, bh, idesc, (kb > q.kb0 || k > 0) ? 1u : 0u);
+              const uint64_t ah = ad + (uint64_t)(k * 2), bh = bd + (uint64_t)(k * 2);
+              mma_ss_pair_elect(tacc, ah, bh, idesc, (kb > q.kb0 || k > 0) ? 1u : 0u);
               if (X3) {
-                mma_f16_ss_pair(tacc, make_desc_k_sw128(a_addr + Cfg::A_BYTES + k * 32), bh, idesc, 1u);     // lo * hi
-                mma_f16_ss_pair(tacc, ah, make_desc_k_sw128(b_addr + Cfg::B_BYTES + k * 32), idesc, 1u);     // hi * lo
+                mma_ss_pair_elect(tacc, ah + (uint64_t)(Cfg::A_BYTES >> 4), bh, idesc, 1u);                 // lo * hi
+                mma_ss_pair_elect(tacc, ah, bh + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);                 // hi * lo
               }
             }
-            mma_commit_pair(&empty[s]);                          // frees stage s in both CTAs
+            mma_commit_pair_elect(&empty[s]);                    // frees stage s in both CTAs
           }
-          mma_commit_pair(&acc_full[buf]);                       // the accumulators of both CTAs are complete
+          mma_commit_pair_elect(&acc_full[buf]);                 // the accumulators of both CTAs are complete
         }
       }
       __syncwarp();

@@ -40,6 +40,11 @@ int attention_tc_multi(const void* q, int ldq, const void* const* k, int ldk, co
                        __nv_bfloat16* const* o_lo, int ldo, const int* kv_div, int nctx, int nsamp, int heads, int T, int d, float scale,
                        int f16, cudaStream_t st);
 
+// ---- internal: head dim 256 on a CTA pair (attn_pair.cu), 128-key steps, P read from tensor memory.  DVD_ATTN_V1=1 disables it.
+bool attention_pair_supported(int T, int d, int nctx);
+int attention_pair(const void* q, int ldq, const void* k, int ldk, const void* vt, __nv_bfloat16* o, __nv_bfloat16* o_lo, int ldo, int nsamp,
+                   int heads, int T, float scale, int kv_div, int f16, cudaStream_t st);
+
 // V [nsamp, T, C] (row stride ldv) -> V^T [nsamp, C, T], any 16-bit type  (test hook only)
 int transpose_v16(const void* v, int ldv, void* vt, int nsamp, int T, int C, cudaStream_t st);
 
