@@ -74,7 +74,8 @@ extern "C" int dvd_test_gemm(const float* A, const float* W, const float* bias, 
     p.e = e;
     return gemm_f32(p, A_DIRECT, B_NK, 1, st);
   }
-  const bool x3 = precision == DVD_PREC_BF16X3;
+  const bool a16 = precision == 3;                // test-only code: ONE fp16 activation x fp16 weight pair (the decoder's q|k|v GEMM in DVD_PREC_BF16X3)
+  const bool x3 = precision == DVD_PREC_BF16X3 || a16;
   auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
   const size_t a_b = al((size_t)M * K * 2), w_b = al((size_t)N * K * 2);
   const size_t ops = (x3 ? 2 : 1) * (a_b + w_b);
@@ -85,8 +86,12 @@ extern "C" int dvd_test_gemm(const float* A, const float* W, const float* bias, 
   int rc;
   if (x3) {
     a.lo = (__nv_bfloat16*)(base + a_b + w_b); w.lo = (__nv_bfloat16*)(base + 2 * a_b + w_b);
-    rc = f32_split_bf16(A, (__nv_bfloat16*)a.hi, (__nv_bfloat16*)a.lo, (long long)M * K, st); if (rc) return rc;
-    rc = f32_split_bf16(W, (__nv_bfloat16*)w.hi, (__nv_bfloat16*)w.lo, (long long)N * K, st); if (rc) return rc;
+    if (a16) { rc = f32_to_f16(A, (void*)a.hi, (long long)M * K, st); a.lo = nullptr; a.f16 = true; }
+    else rc = f32_split_bf16(A, (__nv_bfloat16*)a.hi, (__nv_bfloat16*)a.lo, (long long)M * K, st);
+    if (rc) return rc;
+    rc = a16 ? f32_split_f16(W, (void*)w.hi, (void*)w.lo, (long long)N * K, st)
+             : f32_split_bf16(W, (__nv_bfloat16*)w.hi, (__nv_bfloat16*)w.lo, (long long)N * K, st);
+    if (rc) return rc;
   } else {
     rc = f32_to_bf16(A, (__nv_bfloat16*)a.hi, (long long)M * K, st); if (rc) return rc;
     rc = f32_to_bf16(W, (__nv_bfloat16*)w.hi, (long long)N * K, st); if (rc) return rc;
@@ -146,6 +151,7 @@ extern "C" int dvd_gemm_bf16(const void* A16, const void* A16_lo, int lda, const
   Epilogue e; e.bias = bias; e.out_bf16 = (__nv_bfloat16*)out16; e.ldc_bf16 = N; e.out = out32; e.ldc = N;
   TcMat a, w;
   a.hi = (const __nv_bfloat16*)A16; a.lo = (const __nv_bfloat16*)A16_lo; a.ld = lda;
+  a.f16 = !A16_lo && W16_lo;                      // a lone A next to a weight pair is fp16: the two-pass mode
   w.hi = (const __nv_bfloat16*)W16; w.lo = (const __nv_bfloat16*)W16_lo; w.ld = ldw;
   return gemm_tc(a, w, M, N, K, e, (cudaStream_t)stream);
 }

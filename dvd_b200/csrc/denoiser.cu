@@ -145,16 +145,17 @@ enum { PC_GEMM = 0, PC_ATTN = 1, PC_CONV = 2, PC_COUNT = 3 };
 struct Profiler {
   bool on = false;
   std::vector<cudaEvent_t> ev[PC_COUNT];      // start/stop pairs
-  double flops[PC_COUNT] = {0, 0, 0};
+  double flops[PC_COUNT] = {0, 0, 0};         // algorithmic (2 M N K)
+  double exec_flops[PC_COUNT] = {0, 0, 0};    // what the tensor pipe executes: x3 / x2 in the split-precision passes
   long long launches[PC_COUNT] = {0, 0, 0};
 };
 static thread_local Profiler g_prof;
 struct ProfScope {
   int cls; cudaStream_t st; bool on;
-  ProfScope(int c, cudaStream_t s, double flops) : cls(c), st(s), on(g_prof.on) {
+  ProfScope(int c, cudaStream_t s, double flops, int passes = 1) : cls(c), st(s), on(g_prof.on) {
     if (!on) return;
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_prof.ev[cls].push_back(e);
-    g_prof.flops[cls] += flops; g_prof.launches[cls] += 1;
+    g_prof.flops[cls] += flops; g_prof.exec_flops[cls] += flops * passes; g_prof.launches[cls] += 1;
   }
   ~ProfScope() {
     if (!on) return;
@@ -178,13 +179,14 @@ static void out_operand(Epilogue& e, const B16& dst, int ld) { e.out_bf16 = dst.
 static void out_attn(const Ctx& c, Epilogue& e, __nv_bfloat16* dst, int ld) { e.out_bf16 = dst; e.out_lo = nullptr; e.ldc_bf16 = ld; e.out_f16 = c.x3() ? 1 : 0; }
 
 // C = epi(A * W[row0 : row0+N, :]^T)
+// a_f16 (DVD_PREC_BF16X3 only): A16.hi holds ONE fp16 value per element -> two tensor passes (fp16 A x weight hi, x weight lo)
 static int linear(const Ctx& c, const float* A32, const B16& A16, int lda, const dvd_mat_t& W, int row0, int M, int N,
-                  const Epilogue& e) {
-  ProfScope ps(PC_GEMM, c.st, 2.0 * M * N * W.k);
+                  const Epilogue& e, bool a_f16 = false) {
+  ProfScope ps(PC_GEMM, c.st, 2.0 * M * N * W.k, c.x3() ? (a_f16 ? 2 : 3) : 1);
   if (c.tc()) {
-    DVD_REQUIRE(A16.hi && W.bf16 && (!c.x3() || (A16.lo && W.bf16_lo)), "linear: 16-bit operands missing");
+    DVD_REQUIRE(A16.hi && W.bf16 && (!c.x3() || ((A16.lo || a_f16) && W.bf16_lo)), "linear: 16-bit operands missing");
     TcMat a, w;
-    a.hi = A16.hi; a.lo = c.x3() ? A16.lo : nullptr; a.ld = lda;
+    a.hi = A16.hi; a.lo = (c.x3() && !a_f16) ? A16.lo : nullptr; a.ld = lda; a.f16 = c.x3() && a_f16;
     w.hi = (const __nv_bfloat16*)W.bf16 + (size_t)row0 * W.k; w.ld = W.k;
     w.lo = c.x3() ? (const __nv_bfloat16*)W.bf16_lo + (size_t)row0 * W.k : nullptr;
     return gemm_tc(a, w, M, N, W.k, e, c.st);
@@ -229,7 +231,7 @@ static int static_forward(const Ctx& c, const float* y512, const float* mask_cat
     Q.hi = (__nv_bfloat16*)s.pyrQ; Q.lo = x3 ? Q.hi + half : nullptr;
     auto op = [&](const B16& b) { TcMat m; m.hi = b.hi; m.lo = b.lo; m.ld = 64; return m; };
     {
-      ProfScope ps(PC_CONV, st, 2.0 * B * 512 * 512 * 64 * 36.0);
+      ProfScope ps(PC_CONV, st, 2.0 * B * 512 * 512 * 64 * 36.0, x3 ? 3 : 1);
       DVD_REQUIRE(w.pyr[0].bf16 && (!x3 || w.pyr[0].bf16_lo), "pyramid level_0 16-bit (K-padded) weight missing");
       DVD_TRY(im2col3x3_c4_bf16(s.y4, Q.hi, Q.lo, B, 512, 512, st));                  // Q: [B*512*512, 64]
       Epilogue e; e.bias = w.pyr_b[0]; e.act = ACT_RELU; out_operand(e, P, 64);
@@ -238,7 +240,7 @@ static int static_forward(const Ctx& c, const float* y512, const float* mask_cat
     }
     auto conv = [&](const B16& in, const B16& out, int H, int Cin, int layer) -> int {
       const int Cout = w.pyr[layer].n;
-      ProfScope ps(PC_CONV, st, 2.0 * B * H * H * Cout * 9.0 * Cin);
+      ProfScope ps(PC_CONV, st, 2.0 * B * H * H * Cout * 9.0 * Cin, x3 ? 3 : 1);
       Epilogue e; e.bias = w.pyr_b[layer]; e.act = ACT_RELU; out_operand(e, out, Cout);
       DVD_REQUIRE(w.pyr[layer].bf16 && (!x3 || w.pyr[layer].bf16_lo), "pyramid 16-bit weights missing");
       return conv3x3_tc(op(in), weight_op(c, w.pyr[layer]), B, H, H, Cin, Cout, e, st);
@@ -304,6 +306,10 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
   // at 16 documents in flight, so the separate LayerNorm kernels stay the default.
   const int want_lnf = getenv("DVD_LN_FUSION") ? atoi(getenv("DVD_LN_FUSION")) : 0;
   const bool lnf = c.x3() && want_lnf && w.dec[0].qkv_ln.bf16 && w.dec[0].qkv_ln.bf16_lo;
+  // The decoder's q|k|v GEMM (the largest of the step) takes its activation as ONE fp16 value: q, k and v are rounded to fp16 for the
+  // attention anyway, and what moves the map is weight rounding, not activation rounding (oracle/precision_study.py
+  // --decoder-breakdown: 1.44e-6 -> 1.52e-6 mean map error).  Two tensor passes instead of three.  DVD_QKV_3PASS=1 restores the pair.
+  const bool qkv_a16 = c.x3() && !lnf && w.dec[0].qkv_h.bf16 && w.dec[0].qkv_h.bf16_lo && !(getenv("DVD_QKV_3PASS") && atoi(getenv("DVD_QKV_3PASS")));
   const float* ada = trow + 384;                 // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
   const float* fin = trow + 384 + 2304;          // shift[1536], scale[1536]
   auto off16 = [](const B16& b, size_t n) { B16 r; r.hi = b.hi + n; r.lo = b.lo ? b.lo + n : nullptr; return r; };
@@ -392,7 +398,8 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
   // ---- 6 decoder layers (CA:377-396)
   for (int l = 0; l < 6; ++l) {
     const dvd_dec_layer_t& L = w.dec[l];
-    if (!lnf) DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n1_w, L.n1_b, nullptr, nullptr, st));
+    if (!lnf) DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n1_w, L.n1_b, nullptr, nullptr, st,
+                                qkv_a16 ? 1 : 0));
     {
       Epilogue e; e.out = tc ? nullptr : s.qkv_d; e.ldc = 4608;
       if (tc) { out_attn(c, e, s.qkv_d16, 4608); e.vt_out = s.vt_d16; e.vt_col0 = 3072; }
@@ -400,7 +407,7 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
         e.ln_stats = s.lnstats; e.ln_colsum = L.qkv_colsum; e.ln_chunks = 48; e.ln_eps = 1e-5f; e.bias = L.qkv_cvec;
         DVD_TRY(linear(c, nullptr, s.X16, 1536, L.qkv_ln, 0, M, 4608, e));
       } else {
-        DVD_TRY(linear(c, s.hd, s.hd16, 1536, L.qkv, 0, M, 4608, e));
+        DVD_TRY(linear(c, s.hd, s.hd16, 1536, qkv_a16 ? L.qkv_h : L.qkv, 0, M, 4608, e, qkv_a16));
       }
     }
     DVD_TRY(attention(c, s.qkv_d, s.qkv_d16, 4608, s.qkv_d + 1536, tc ? s.qkv_d16 + 1536 : nullptr, 4608, s.qkv_d + 3072, s.vt_d16, 4608,
@@ -521,12 +528,12 @@ extern "C" int dvd_debug_stop_after(int stage) { g_stop_after = stage; return 0;
 
 extern "C" int dvd_profile_begin(void) {
   for (auto& v : g_prof.ev) { for (auto e : v) cudaEventDestroy(e); v.clear(); }
-  for (int i = 0; i < PC_COUNT; ++i) { g_prof.flops[i] = 0; g_prof.launches[i] = 0; }
+  for (int i = 0; i < PC_COUNT; ++i) { g_prof.flops[i] = 0; g_prof.exec_flops[i] = 0; g_prof.launches[i] = 0; }
   g_prof.on = true;
   return 0;
 }
-// ms[3], flops[3], launches[3] for the classes {gemm, attention, pyramid conv}; synchronises the device.
-extern "C" int dvd_profile_end(double* ms, double* flops, long long* launches) {
+// ms[3], flops[3], launches[3], executed_flops[3] for the classes {gemm, attention, pyramid conv}; synchronises the device.
+extern "C" int dvd_profile_end(double* ms, double* flops, long long* launches, double* executed_flops) {
   g_prof.on = false;
   DVD_CUDA(cudaDeviceSynchronize());
   for (int c = 0; c < PC_COUNT; ++c) {
@@ -536,6 +543,7 @@ extern "C" int dvd_profile_end(double* ms, double* flops, long long* launches) {
     }
     if (ms) ms[c] = tot;
     if (flops) flops[c] = g_prof.flops[c];
+    if (executed_flops) executed_flops[c] = g_prof.exec_flops[c];
     if (launches) launches[c] = g_prof.launches[c];
     for (auto e : g_prof.ev[c]) cudaEventDestroy(e);
     g_prof.ev[c].clear();

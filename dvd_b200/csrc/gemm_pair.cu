@@ -38,13 +38,17 @@ constexpr int PP_EPI_WARPS = 8;
 constexpr int PP_REGS_CTRL = 56, PP_REGS_EPI = 224;
 static_assert(128 * PP_REGS_CTRL + 256 * PP_REGS_EPI <= 65536, "register budget after setmaxnreg");
 
-template <int BN, bool X3>
+// MODE: 0 = bf16 x bf16 (one pass); 1 = split pairs on both sides (hi*hi + lo*hi + hi*lo, DVD_PREC_BF16X3); 2 = ONE fp16 activation
+// operand x fp16 weight pair (hi + lo): two passes, for the GEMMs whose activation tolerates fp16 rounding (oracle/precision_study.py
+// --decoder-breakdown: it is the WEIGHT rounding that moves the map, the same perturbation for every token and step).  Everything is
+// IEEE fp16 in this mode: kind::f16 rejects an fp16 A next to a bf16 B (illegal instruction, tried).
+template <int BN, int MODE>
 struct PairCfg {
-  static constexpr int NOP = X3 ? 2 : 1;
+  static constexpr int NA = MODE == 1 ? 2 : 1, NB = MODE >= 1 ? 2 : 1;
   static constexpr int A_BYTES = PBM * PBK * 2;                 // 16 KB: this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * PBK * 2;            // this CTA's half of the W tile
-  static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
-  static constexpr int B_OFF = NOP * A_BYTES;
+  static constexpr int STAGE_BYTES = NA * A_BYTES + NB * B_BYTES;
+  static constexpr int B_OFF = NA * A_BYTES;
   static constexpr int FIXED = 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int STAGES_FIT = (232448 - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
@@ -384,11 +388,11 @@ __device__ __forceinline__ void epilogue_loop(const PairParams& p, const Epilogu
   }
 }
 
-template <int BN, bool X3, bool CONV>
+template <int BN, int MODE, bool CONV>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmBl, const PairParams p, const Epilogue e) {
-  using Cfg = PairCfg<BN, X3>;
+  using Cfg = PairCfg<BN, MODE>;
   constexpr int ST = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -407,7 +411,8 @@ k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     PTRACE(0);                                               // CTA start
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
-    if (X3) { prefetch_tmap(&tmAl); prefetch_tmap(&tmBl); }
+    if (MODE == 1) prefetch_tmap(&tmAl);
+    if (MODE >= 1) prefetch_tmap(&tmBl);
     for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }       // full: the leader's arrive.expect_tx; both CTAs' TMA bytes
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 2 * PP_EPI_WARPS); }
     fence_barrier_init();
@@ -467,14 +472,14 @@ k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t lead_full = mapa(smem_u32(&full[s]), 0);
             if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);        // both CTAs' loads of this stage
   #pragma unroll
-            for (int o = 0; o < Cfg::NOP; ++o) tma_load_2d_pair(a + Cfg::B_OFF + o * Cfg::B_BYTES, o ? &tmBl : &tmB, lead_full, kb * PBK, nb);
+            for (int o = 0; o < Cfg::NB; ++o) tma_load_2d_pair(a + Cfg::B_OFF + o * Cfg::B_BYTES, o ? &tmBl : &tmB, lead_full, kb * PBK, nb);
           };
           auto load_a = [&](int kb, uint32_t gg) {
             const int s = gg % ST;
             uint8_t* a = smem + s * Cfg::STAGE_BYTES;
             const uint32_t lead_full = mapa(smem_u32(&full[s]), 0);
   #pragma unroll
-            for (int o = 0; o < Cfg::NOP; ++o) {
+            for (int o = 0; o < Cfg::NA; ++o) {
               if (CONV) {
                 const int tap = kb / cblocks, cb = kb - tap * cblocks;
                 tma_load_4d_pair(a + o * Cfg::A_BYTES, o ? &tmAl : &tmA, lead_full, cb * 64, cx + tap % 3 - 1, cy + tap / 3 - 1, cn);
@@ -508,7 +513,7 @@ k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (rank == 0) {
         // ===== MMA issuer (leader only): UMMA M = 256 across the pair, accumulator buffer = unit parity.  The whole warp runs the loop
         // and one elected lane issues (tc_common.cuh: inside an `if (lane == 0)` region every UMMA costs an elect / branch loop).
-        constexpr uint32_t idesc = make_idesc_bf16(2 * PBM, BN);
+        constexpr uint32_t idesc = MODE == 2 ? make_idesc_f16(2 * PBM, BN) : make_idesc_bf16(2 * PBM, BN);
         const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);       // warp-uniform for the compiler
         uint32_t g = 0;
         int it = 0;
@@ -532,10 +537,8 @@ k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int k = 0; k < PBK / 16; ++k) {
               const uint64_t ah = ad + (uint64_t)(k * 2), bh = bd + (uint64_t)(k * 2);
               mma_ss_pair_elect(tacc, ah, bh, idesc, (kb > q.kb0 || k > 0) ? 1u : 0u);
-              if (X3) {
-                mma_ss_pair_elect(tacc, ah + (uint64_t)(Cfg::A_BYTES >> 4), bh, idesc, 1u);                 // lo * hi
-                mma_ss_pair_elect(tacc, ah, bh + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);                 // hi * lo
-              }
+              if (MODE == 1) mma_ss_pair_elect(tacc, ah + (uint64_t)(Cfg::A_BYTES >> 4), bh, idesc, 1u);    // lo * hi
+              if (MODE >= 1) mma_ss_pair_elect(tacc, ah, bh + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);    // hi * lo
             }
             mma_commit_pair_elect(&empty[s]);                    // frees stage s in both CTAs
           }
@@ -569,20 +572,20 @@ static bool epilogue_periods_ok(const Epilogue& e) {
   return (e.resid_mod % 128 == 0) && (e.pos_rows % 128 == 0) && (e.group_rows % 128 == 0);
 }
 
-template <int BN, bool X3, bool CONV>
+template <int BN, int MODE, bool CONV>
 static int max_pairs() {           // co-resident clusters of this instantiation on the current device (cached per device)
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
   if (cached[dev]) return cached[dev];
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * 256); cfg.blockDim = dim3(PP_THREADS); cfg.dynamicSmemBytes = PairCfg<BN, X3>::SMEM;
+  cfg.gridDim = dim3(2 * 256); cfg.blockDim = dim3(PP_THREADS); cfg.dynamicSmemBytes = PairCfg<BN, MODE>::SMEM;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, k_gemm_pair<BN, X3, CONV>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sm_count() / 2 - 2; }
+  if (cudaOccupancyMaxActiveClusters(&n, k_gemm_pair<BN, MODE, CONV>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sm_count() / 2 - 2; }
   if (n > sm_count() / 2) n = sm_count() / 2;
   cached[dev] = n;
   return n;
@@ -592,14 +595,14 @@ static int max_pairs() {           // co-resident clusters of this instantiation
 // x3 in split-precision mode) against the L2 -> SM operand stream (~43 B/clk per SM when every SM pulls: 12.5 TB/s measured with
 // tools/gemm_trace.py).  Per unit a fixed pipeline-fill cost, per launch the exposed last epilogue.  Calibrated against
 // profiles/r2_gemm_sweep.txt (all denoiser shapes x {128,192,256}).
-static double unit_kb_cycles(int bn, bool x3) {
-  const double mma = (x3 ? 3.0 : 1.0) * 4.0 * (bn / 2.0) * 1.15;
-  const double bytes = (x3 ? 2.0 : 1.0) * (16384.0 + bn * 64.0);
+static double unit_kb_cycles(int bn, int mode) {
+  const double mma = (mode == 1 ? 3.0 : mode == 2 ? 2.0 : 1.0) * 4.0 * (bn / 2.0) * 1.15;
+  const double bytes = (mode == 1 ? 2.0 : 1.0) * 16384.0 + (mode >= 1 ? 2.0 : 1.0) * bn * 64.0;
   const double mem = bytes / 43.0;
   return mma > mem ? mma : mem;
 }
 
-static int pick_bn(int M, int N, int K, bool x3, int npairs) {
+static int pick_bn(int M, int N, int K, int mode, int npairs) {
   const int nkb = (K + PBK - 1) / PBK;
   double best = -1.0;
   int bn_out = 64;
@@ -610,19 +613,19 @@ static int pick_bn(int M, int N, int K, bool x3, int npairs) {
     if (g_force_bn > 0 && bn != g_force_bn && N % g_force_bn == 0) continue;
     const long long units = (long long)(M / 256) * (N / bn);
     const long long waves = (units + npairs - 1) / npairs;
-    const double cost = waves * (nkb * unit_kb_cycles(bn, x3) + 700.0) + (900.0 + 9.0 * bn);
+    const double cost = waves * (nkb * unit_kb_cycles(bn, mode) + 700.0) + (900.0 + 9.0 * bn);
     if (best < 0 || cost < best) { best = cost; bn_out = bn; }
   }
   return bn_out;
 }
 
-template <int BN, bool X3, bool CONV>
+template <int BN, int MODE, bool CONV>
 static int launch_pair(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, int conv_b, int conv_h, int conv_w, int conv_cin,
                        cudaStream_t st) {
-  using Cfg = PairCfg<BN, X3>;
-  auto kern = k_gemm_pair<BN, X3, CONV>;
+  using Cfg = PairCfg<BN, MODE>;
+  auto kern = k_gemm_pair<BN, MODE, CONV>;
   DVD_SET_MAX_SMEM(kern, Cfg::SMEM);
-  const int npairs_max = max_pairs<BN, X3, CONV>();
+  const int npairs_max = max_pairs<BN, MODE, CONV>();
   DVD_REQUIRE(npairs_max > 0, "gemm_pair: no co-resident cluster available");
   CUtensorMap tmA, tmB, tmAl, tmBl;
   int rc;
@@ -631,10 +634,12 @@ static int launch_pair(const TcMat& A, const TcMat& W, int M, int N, int K, cons
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, W.hi, (uint64_t)N, (uint64_t)K, (uint64_t)W.ld, (uint32_t)(BN / 2), 64); if (rc) return rc;
   tmAl = tmA; tmBl = tmB;
-  if (X3) {
+  if (MODE == 1) {
     if (CONV) rc = make_tmap_bf16_nhwc(&tmAl, A.lo, (uint64_t)conv_b, (uint64_t)conv_h, (uint64_t)conv_w, (uint64_t)conv_cin);
     else rc = make_tmap_bf16_2d(&tmAl, A.lo, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, 128, 64);
     if (rc) return rc;
+  }
+  if (MODE >= 1) {
     rc = make_tmap_bf16_2d(&tmBl, W.lo, (uint64_t)N, (uint64_t)K, (uint64_t)W.ld, (uint32_t)(BN / 2), 64); if (rc) return rc;
   }
   PairParams p;
@@ -646,21 +651,21 @@ static int launch_pair(const TcMat& A, const TcMat& W, int M, int N, int K, cons
   p.npairs = units < npairs_max ? (int)units : npairs_max;
   p.conv_h = conv_h; p.conv_w = conv_w; p.conv_cin = conv_cin;
   p.epi = classify_epilogue(e);
-  if (g_debug) fprintf(stderr, "[gemm_pair] M=%d N=%d K=%d x3=%d conv=%d bn=%d units=%d npairs=%d (max %d) stages=%d smem=%d\n", M, N, K,
-                       (int)X3, (int)CONV, BN, p.units, p.npairs, npairs_max, Cfg::STAGES, Cfg::SMEM);
+  if (g_debug) fprintf(stderr, "[gemm_pair] M=%d N=%d K=%d mode=%d conv=%d bn=%d units=%d npairs=%d (max %d) stages=%d smem=%d\n", M, N, K,
+                       MODE, (int)CONV, BN, p.units, p.npairs, npairs_max, Cfg::STAGES, Cfg::SMEM);
   DVD_CUDA(launch_pdl_cluster(1, kern, dim3(2 * p.npairs), dim3(PP_THREADS), (size_t)Cfg::SMEM, st, 2, 1, tmA, tmAl, tmB, tmBl, p, e));
   DVD_LAUNCH_CHECK("k_gemm_pair");
   return 0;
 }
 
-template <bool X3, bool CONV>
+template <int MODE, bool CONV>
 static int launch_pair_bn(int bn, const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, int conv_b, int conv_h, int conv_w,
                           int conv_cin, cudaStream_t st) {
   switch (bn) {
-    case 256: return launch_pair<256, X3, CONV>(A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
-    case 192: return launch_pair<192, X3, CONV>(A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
-    case 128: return launch_pair<128, X3, CONV>(A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
-    default:  return launch_pair<64, X3, CONV>(A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
+    case 256: return launch_pair<256, MODE, CONV>(A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
+    case 192: return launch_pair<192, MODE, CONV>(A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
+    case 128: return launch_pair<128, MODE, CONV>(A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
+    default:  return launch_pair<64, MODE, CONV>(A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
   }
 }
 
@@ -670,7 +675,10 @@ static int launch_pair_bn(int bn, const TcMat& A, const TcMat& W, int M, int N, 
 int gemm_pair_dispatch(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, int conv_b, int conv_h, int conv_w, int conv_cin,
                        cudaStream_t st) {
   read_env();
-  const bool conv = conv_h > 0, x3 = A.lo != nullptr;
+  const bool conv = conv_h > 0;
+  const int mode = A.lo ? 1 : (A.f16 ? 2 : 0);
+  DVD_REQUIRE(mode == 0 || W.lo, "gemm_pair: the weight's low half is missing");
+  DVD_REQUIRE(mode != 2 || !conv, "gemm_pair: the fp16-activation mode has no implicit-GEMM instantiation");
   DVD_REQUIRE(gemm_pair_supported(M, N, K, conv), "gemm_pair: unsupported shape M=%d N=%d K=%d", M, N, K);
   DVD_REQUIRE(epilogue_periods_ok(e), "gemm_pair: resid_mod / pos_rows / group_rows must be multiples of 128");
   DVD_REQUIRE((!e.ln_stats && !e.stats_out) || classify_epilogue(e) != EPI_GENERIC, "gemm_pair: fused-LN / row-statistics epilogue combination not compiled");
@@ -678,11 +686,12 @@ int gemm_pair_dispatch(const TcMat& A, const TcMat& W, int M, int N, int K, cons
               "gemm_pair: fused LN needs ln_colsum and an even number of 32-column chunks");
   DVD_REQUIRE(!e.stats_out || (N % 32 == 0 && !e.group_rows), "gemm_pair: row statistics need N %% 32 == 0 and no stream remap");
   DVD_REQUIRE(!conv || (conv_w % 128 == 0 && conv_cin % 64 == 0 && K == 9 * conv_cin), "gemm_pair: bad conv geometry");
-  const int bn = pick_bn(M, N, K, x3, sm_count() / 2);
-  if (conv) return x3 ? launch_pair_bn<true, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st)
-                      : launch_pair_bn<false, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
-  return x3 ? launch_pair_bn<true, false>(bn, A, W, M, N, K, e, 0, 0, 0, 0, st)
-            : launch_pair_bn<false, false>(bn, A, W, M, N, K, e, 0, 0, 0, 0, st);
+  const int bn = pick_bn(M, N, K, mode, sm_count() / 2);
+  if (conv) return mode ? launch_pair_bn<1, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st)
+                        : launch_pair_bn<0, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
+  if (mode == 2) return launch_pair_bn<2, false>(bn, A, W, M, N, K, e, 0, 0, 0, 0, st);
+  return mode ? launch_pair_bn<1, false>(bn, A, W, M, N, K, e, 0, 0, 0, 0, st)
+              : launch_pair_bn<0, false>(bn, A, W, M, N, K, e, 0, 0, 0, 0, st);
 }
 
 }  // namespace dvd

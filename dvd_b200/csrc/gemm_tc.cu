@@ -360,11 +360,13 @@ static int launch_tc_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmAl,
 int gemm_tc(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue& e, cudaStream_t st) {
   DVD_REQUIRE(A.hi && W.hi && (e.out || e.out_bf16), "gemm_tc: null pointer");
   DVD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && M % 128 == 0, "gemm_tc: bad shape M=%d N=%d K=%d (M must be a multiple of 128)", M, N, K);
-  DVD_REQUIRE((A.lo != nullptr) == (W.lo != nullptr), "gemm_tc: A and W must both be split pairs or both plain");
+  DVD_REQUIRE(A.f16 ? (!A.lo && W.lo) : ((A.lo != nullptr) == (W.lo != nullptr)),
+              "gemm_tc: A and W must both be split pairs or both plain (or: fp16 A with a weight pair)");
   int rc = check_epilogue(e, N); if (rc) return rc;
   const bool periods_ok = e.resid_mod % 128 == 0 && e.pos_rows % 128 == 0 && e.group_rows % 128 == 0;
   if (!use_v1() && periods_ok && gemm_pair_supported(M, N, K, false)) return gemm_pair_dispatch(A, W, M, N, K, e, 0, 0, 0, 0, st);
   DVD_REQUIRE(!e.ln_stats && !e.stats_out, "gemm_tc: fused LayerNorm / row statistics need the CTA-pair kernel (M %% 256 == 0, N %% 64 == 0)");
+  DVD_REQUIRE(!A.f16, "gemm_tc: the fp16-activation mode needs the CTA-pair kernel (M %% 256 == 0, N %% 64 == 0)");
   const bool x3 = A.lo != nullptr;
   // wide tiles only when they still fill the machine
   const bool wide = (N % 256 == 0) && ((long long)(M / 128) * (N / 256) * 100 >= 190LL * sm_count());

@@ -13,6 +13,7 @@ struct TcMat {
   const __nv_bfloat16* hi = nullptr;
   const __nv_bfloat16* lo = nullptr;
   int ld = 0;
+  bool f16 = false;      // A: `hi` holds ONE IEEE fp16 value per element (two-pass mode; lo must be null, and W must be an fp16 pair)
 };
 
 // C[M,N] = epilogue(A[M,K] * W[N,K]^T), fp32 accumulate in TMEM.  M % 128 == 0, K % 8 == 0, N % 4 == 0.

@@ -9,7 +9,7 @@ template <int NV>   // float4 per lane: C = 128 * NV
 __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ in, int ldin, float* __restrict__ out, int ldo,
                                                    __nv_bfloat16* __restrict__ out16, __nv_bfloat16* __restrict__ out16_lo, int ldo16,
                                                    int rows, float eps, const float* __restrict__ w, const float* __restrict__ b,
-                                                   const float* __restrict__ msh, const float* __restrict__ msc) {
+                                                   const float* __restrict__ msh, const float* __restrict__ msc, int f16) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -44,22 +44,26 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ in,
     if (out) *reinterpret_cast<float4*>(out + (size_t)row * ldo + c0) = make_float4(y[0], y[1], y[2], y[3]);
     if (out16) {
       uint2 u, l;
-      split_bf16x2(y[0], y[1], u.x, l.x);
-      split_bf16x2(y[2], y[3], u.y, l.y);
+      if (f16) {                               // single IEEE fp16 operand (two-pass GEMM: fp16 activation x weight pair)
+        u.x = pack_f16x2(y[0], y[1]); u.y = pack_f16x2(y[2], y[3]);
+      } else {
+        split_bf16x2(y[0], y[1], u.x, l.x);
+        split_bf16x2(y[2], y[3], u.y, l.y);
+      }
       *reinterpret_cast<uint2*>(out16 + (size_t)row * ldo16 + c0) = u;
-      if (out16_lo) *reinterpret_cast<uint2*>(out16_lo + (size_t)row * ldo16 + c0) = l;
+      if (out16_lo && !f16) *reinterpret_cast<uint2*>(out16_lo + (size_t)row * ldo16 + c0) = l;
     }
   }
 }
 
 int layernorm(const float* in, int ldin, float* out, int ldo, __nv_bfloat16* out16, __nv_bfloat16* out16_lo, int ldo16, int rows, int C,
-              float eps, const float* w, const float* b, const float* msh, const float* msc, cudaStream_t st) {
+              float eps, const float* w, const float* b, const float* msh, const float* msc, cudaStream_t st, int out_f16) {
   DVD_REQUIRE(in && (out || out16) && rows > 0, "layernorm: bad args");
   DVD_REQUIRE(C == 384 || C == 1536, "layernorm: C must be 384 or 1536 (got %d)", C);
   DVD_REQUIRE(ldin % 4 == 0 && ldo % 4 == 0 && ldo16 % 4 == 0, "layernorm: ld %% 4");
   dim3 grid(cdiv(rows, 8));
-  if (C == 384) DVD_CUDA(launch_pdl(4, k_layernorm<3>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, out16_lo, ldo16, rows, eps, w, b, msh, msc));
-  else          DVD_CUDA(launch_pdl(4, k_layernorm<12>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, out16_lo, ldo16, rows, eps, w, b, msh, msc));
+  if (C == 384) DVD_CUDA(launch_pdl(4, k_layernorm<3>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, out16_lo, ldo16, rows, eps, w, b, msh, msc, out_f16));
+  else          DVD_CUDA(launch_pdl(4, k_layernorm<12>, grid, dim3(256), (size_t)0, st, in, ldin, out, ldo, out16, out16_lo, ldo16, rows, eps, w, b, msh, msc, out_f16));
   DVD_LAUNCH_CHECK("k_layernorm");
   return 0;
 }
@@ -830,6 +834,19 @@ __global__ void k_f32_to_f16(const float* __restrict__ in, __half* __restrict__ 
 int f32_to_f16(const float* in, void* out, long long n, cudaStream_t st) {
   k_f32_to_f16<<<cdiv(n, 256), 256, 0, st>>>(in, (__half*)out, n);
   DVD_LAUNCH_CHECK("k_f32_to_f16");
+  return 0;
+}
+__global__ void k_f32_split_f16(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = in[i];
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+int f32_split_f16(const float* in, void* hi, void* lo, long long n, cudaStream_t st) {
+  k_f32_split_f16<<<cdiv(n, 256), 256, 0, st>>>(in, (__half*)hi, (__half*)lo, n);
+  DVD_LAUNCH_CHECK("k_f32_split_f16");
   return 0;
 }
 // out = hi (+ lo)

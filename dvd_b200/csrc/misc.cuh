@@ -10,7 +10,8 @@ namespace dvd {
 // bf16 destinations throughout this header: `x16` alone is plain bf16; with a non-null `x16_lo` the value is stored as the split
 // pair hi = bf16(v), lo = bf16(v - hi) (operand of a 3-pass GEMM in DVD_PREC_BF16X3).
 int layernorm(const float* in, int ldin, float* out, int ldo, __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_lo, int ldo16, int rows, int C,
-              float eps, const float* w, const float* b, const float* mod_shift, const float* mod_scale, cudaStream_t st);
+              float eps, const float* w, const float* b, const float* mod_shift, const float* mod_scale, cudaStream_t st, int out_f16 = 0);
+// (out_f16 != 0: out_bf16 receives ONE IEEE fp16 value per element instead of bf16 / a bf16 pair)
 
 // y512 [B,3,512,512] + mask [B,1,512,512] (NCHW) -> NHWC [B,512,512,4]        (CM:586-587)
 int pack_y4(const float* y512, const float* mask, float* out, int B, cudaStream_t st);
@@ -87,5 +88,6 @@ namespace dvd {
 int bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st);
 int f32_split_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t st);
 int f32_to_f16(const float* in, void* out, long long n, cudaStream_t st);
+int f32_split_f16(const float* in, void* hi, void* lo, long long n, cudaStream_t st);      // IEEE fp16 pair (test hook)
 int pair_to_f32(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, long long n, cudaStream_t st);
 }

@@ -180,7 +180,7 @@ class DewarpPipeline:
             peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}; which = "fallback"
         with torch.cuda.device(self.dev):
             flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
-            ms, fl, ln = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)()
+            ms, fl, ln, fx = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)(), (C.c_double * 3)()
             tot_ms, tot = [0.0, 0.0, 0.0], 0.0
             for it in range(iters):
                 flush.fill_(it)
@@ -190,7 +190,7 @@ class DewarpPipeline:
                 self.eng.static_forward(d["y512"], d["mask_cat"], d["mask_y512"], d["line_msk"])
                 self.eng.sample(d["x_T"], self.init_flow0, self.tables, self.t_scaled, self.a, self.b, None, self.map64)
                 e1.record()
-                _lib.check(self.lib.dvd_profile_end(ms, fl, ln), "dvd_profile_end")
+                _lib.check(self.lib.dvd_profile_end(ms, fl, ln, fx), "dvd_profile_end")
                 if it == 0:
                     continue                                        # warm-up
                 tot += e0.elapsed_time(e1)
@@ -206,7 +206,7 @@ class DewarpPipeline:
             except Exception:
                 traffic = {}
             tensor_mode = self.precision in ("bf16", "bf16x3")
-            passes = 3 if self.precision == "bf16x3" else 1
+            exec_tf = fx[0] / (tot_ms[0] / n * 1e-3) / 1e12 if tot_ms[0] > 0 else 0.0
             peak_tf = peaks["bf16_tflops_sustained"] if tensor_mode else 72.0      # fp32 FFMA: 148 SM x 128 FMA x 2 x 1.9 GHz
             roof = {"kernel": "k_gemm_pair: dense GEMM (all linear layers of one step batch)", "bound": "tensor", "achieved": gemm_tf,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
@@ -214,8 +214,9 @@ class DewarpPipeline:
                     "launches_per_step": int(ln[0]), "gflop_per_step": fl[0] / 1e9, "attention_tflops": attn_tf,
                     "attention_gflop_per_step": fl[1] / 1e9,
                     # achieved / frac count ALGORITHMIC flops (2 M N K).  The split-precision mode executes three tensor-core passes per
-                    # k-step to be fp32-accurate, so its tensor pipe does `mma_passes` x that work: frac_executed is the pipe's own load.
-                    "mma_passes": passes, "executed_tflops": gemm_tf * passes, "frac_executed": gemm_tf * passes / peak_tf,
+                    # k-step to be fp32-accurate (two in the decoder's q|k|v GEMM), so its tensor pipe does `mma_passes` x that work on
+                    # average: frac_executed is the pipe's own load.
+                    "mma_passes": round(fx[0] / fl[0], 3) if fl[0] > 0 else 1, "executed_tflops": exec_tf, "frac_executed": exec_tf / peak_tf,
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % which) if tensor_mode else "nominal fp32 FFMA"}
             if not with_unwarp:
                 return {"roofline": roof, "share": share}

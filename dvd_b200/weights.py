@@ -55,6 +55,15 @@ def split_bf16(w: torch.Tensor):
     return hi.contiguous(), lo.contiguous()
 
 
+def split_f16(w: torch.Tensor):
+    """fp32 -> (hi, lo) IEEE fp16 pair (weights of the GEMMs whose activation operand is a single fp16 value)."""
+    if float(w.abs().max()) >= 65504.0:
+        raise ValueError("weight magnitude exceeds the fp16 range")
+    hi = w.to(torch.float16)
+    lo = (w - hi.float()).to(torch.float16)
+    return hi.contiguous(), lo.contiguous()
+
+
 class PackedWeights:
     """Owns the packed device tensors and the ``dvd_weights_t`` table that points into them."""
 
@@ -144,6 +153,12 @@ class PackedWeights:
             L.n2_w, L.n2_b = self._vec(sd[p + "norm2.weight"]), self._vec(sd[p + "norm2.bias"])
             L.qkv = self._mat(torch.cat([sd[p + "attn.linear_q.weight"], sd[p + "attn.linear_k.weight"],
                                          sd[p + "attn.linear_v.weight"]], 0))
+            if self.with_bf16:                                    # fp16 pair of the same weights (two-pass q|k|v GEMM of bf16x3)
+                wq32 = self.keep[-3]                              # the fp32 copy _mat just made (keep = [..., f32, hi, lo])
+                h16, l16 = split_f16(wq32)
+                self.keep += [h16, l16]
+                L.qkv_h.f32, L.qkv_h.bf16, L.qkv_h.bf16_lo = wq32.data_ptr(), h16.data_ptr(), l16.data_ptr()
+                L.qkv_h.n, L.qkv_h.k = 4608, 1536
             L.fc = self._mat(sd[p + "attn.fc.weight"])
             f = p + "feed_forward."
             L.conv1 = self._mat(sd[f + "conv1.conv.weight"].reshape(2048, 1536))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DVD_ABI_VERSION 3
+#define DVD_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define DVD_API __attribute__((visibility("default")))
@@ -70,6 +70,10 @@ typedef struct dvd_dec_layer {          /* CA:343-396 DecoderLayer, CA:13-57 fee
   const float *bn3_scale, *bn3_shift;
   /* LayerNorm folded into the consumer GEMM (DVD_PREC_BF16X3): W' = W * gamma (per input channel), colsum[n] = sum_k W'[n][k] of the
    * ROUNDED pair, cvec = W beta.  The epilogue computes rstd * (x W'^T - mean * colsum) + cvec from the raw residual rows. */
+  /* The q|k|v GEMM of DVD_PREC_BF16X3 takes ONE fp16 activation value per element (two tensor passes instead of three; q, k, v are
+   * rounded to fp16 for the attention anyway).  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, so these weights are ALSO
+   * packed as an IEEE fp16 pair: qkv_h.bf16 = fp16(W), qkv_h.bf16_lo = fp16(W - fp16(W)).  NULL pointers: the three-pass path runs. */
+  dvd_mat_t qkv_h;                      /* [4608,1536], fp16 hi / lo in the bf16 / bf16_lo slots */
   dvd_mat_t qkv_ln;                     /* [4608,1536] = qkv * norm1.weight               */
   const float *qkv_colsum, *qkv_cvec;   /* [4608]                                         */
   dvd_mat_t conv1_ln;                   /* [2048,1536] = conv1 * norm2.weight             */
@@ -190,14 +194,16 @@ DVD_API int dvd_test_attention(const float* q, const float* k, const float* v, f
                        int T, int d, float scale, int precision, void* scratch, size_t scratch_bytes,
                        void* stream);
 /* Plain tensor-core GEMM (tuning / micro-benchmarks): out = A[M,K] W[N,K]^T + bias; bf16 operands (A16_lo / W16_lo non-NULL:
- * split pairs, three passes), bf16 and/or fp32 output. */
+ * split pairs, three passes; A16_lo NULL next to a weight pair: A16, W16 and W16_lo hold IEEE fp16, two passes), bf16 and/or fp32 output.
+ * dvd_test_gemm accepts precision 3 for the same two-pass mode (fp16 activation x fp16 weight pair). */
 DVD_API int dvd_gemm_bf16(const void* A16, const void* A16_lo, int lda, const void* W16, const void* W16_lo, int ldw,
                           const float* bias, void* out16, float* out32, int M, int N, int K, void* stream);
 /* Kernel-class profiler: between begin/end every dense contraction launched by this thread is bracketed by CUDA
  * events.  end() synchronises and returns, for the classes {0: GEMM, 1: attention, 2: pyramid conv}, the summed
- * device time (ms), algorithmic FLOPs and launch counts. */
+ * device time (ms), algorithmic FLOPs (2 M N K), launch counts and the FLOPs the tensor pipe executed (the split-precision
+ * mode runs three passes per k-step, two in the q|k|v GEMM of the decoder).  Any output pointer may be NULL. */
 DVD_API int dvd_profile_begin(void);
-DVD_API int dvd_profile_end(double* ms, double* flops, long long* launches);
+DVD_API int dvd_profile_end(double* ms, double* flops, long long* launches, double* executed_flops);
 /* number of kernel launches issued by this library on this thread since the last reset */
 DVD_API long long dvd_launch_count(int reset);
 

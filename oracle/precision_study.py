@@ -51,14 +51,22 @@ class FProxy:
     @staticmethod
     def linear(x, w, b=None):
         m = Cfg.mode()
-        return TF.linear(rnd(x, m), rnd(w, m), b)
+        return TF.linear(rnd(x, amode(m)), rnd(w, wmode(m)), b)
 
     @staticmethod
     def conv2d(x, w, b=None, **kw):
         m = Cfg.mode()
         if kw.get("groups", 1) > 1:        # depthwise conv is an elementwise kernel in fp32 in every mode
             return TF.conv2d(x, w, b, **kw)
-        return TF.conv2d(rnd(x, m), rnd(w, m), b, **kw)
+        return TF.conv2d(rnd(x, amode(m)), rnd(w, wmode(m)), b, **kw)
+
+
+def amode(m):                              # "a16w3": activations single fp16, weights as a bf16 pair (two passes); "ab16w3": single bf16
+    return {"a16w3": "fp16", "ab16w3": "bf16"}.get(m, m)
+
+
+def wmode(m):
+    return {"a16w3": "x3", "ab16w3": "x3"}.get(m, m)
 
 
 _orig = {}
@@ -128,7 +136,7 @@ def main():
         sys.stdout.flush()
 
 
-if __name__ == "__main__" and "--ln-fusion" not in sys.argv:
+if __name__ == "__main__" and not any(f in sys.argv for f in ("--ln-fusion", "--qkv", "--two-pass", "--decoder-breakdown")):
     main()
 
 
@@ -220,3 +228,120 @@ def ln_fusion_study():
 
 if __name__ == "__main__" and "--ln-fusion" in sys.argv:
     ln_fusion_study()
+
+
+# ----------------------------------------------------------------------------------------------- attention-input GEMM study
+# q, k, v are rounded to fp16 before the attention MMAs anyway (2^-12), so do the GEMMs that PRODUCE them need all three split passes?
+# Cases: the decoder's q|k|v GEMMs (18 of them, the largest GEMM of the step) with only one cross term kept (two passes: either the
+# activation or the weight is a single bf16), or none (one pass).
+def qkv_study():
+    torch.set_num_threads(8)
+    sd = synth.make_state_dict(1234, live_only=True)
+    inp = synth.make_doc_inputs(0, H=192, W=256)
+    inp.pop("photo")
+    patch()
+    ref = run(sd, inp, {})
+    groups = ["pyramid", "embed", "dit", "dit_attn", "decoder", "decoder_attn"]
+    x3 = {**{g: "x3" for g in groups}, "dit_attn": "fp16", "decoder_attn": "fp16"}
+    qkv_ids = {id(sd[f"decoder.layer_stack.{i}.attn.linear_{n}.weight"]) for i in range(6) for n in "qkv"}
+    special = {"x": "x3", "w": "x3"}
+
+    def linear(x, w, b=None):
+        if id(w) in qkv_ids:
+            return TF.linear(rnd(x, special["x"]), rnd(w, special["w"]), b)
+        m = Cfg.mode()
+        return TF.linear(rnd(x, m), rnd(w, m), b)
+    O.F.linear = linear
+    print(f"{'decoder q|k|v GEMM operands':52s} {'mean':>10s} {'max':>10s} {'mean px@4032':>13s} {'max px@4032':>12s}")
+    for name, xm, wm in (("x pair, w pair (3 passes, shipping)", "x3", "x3"), ("x pair, w bf16 (2 passes)", "x3", "bf16"),
+                         ("x bf16, w pair (2 passes)", "bf16", "x3"), ("x bf16, w bf16 (1 pass)", "bf16", "bf16"),
+                         ("x fp16, w fp16 (1 pass, fp16 operands)", "fp16", "fp16")):
+        special["x"], special["w"] = xm, wm
+        out = run(sd, inp, x3)
+        e = (out - ref).abs()
+        print(f"{name:52s} {float(e.mean()):10.3e} {float(e.max()):10.3e} {float(e.mean()) * 2015.5:13.4f} {float(e.max()) * 2015.5:12.4f}")
+        sys.stdout.flush()
+
+
+if __name__ == "__main__" and "--qkv" in sys.argv:
+    qkv_study()
+
+
+# ----------------------------------------------------------------------------------------------- two-pass study
+# The weight rounding is what hurts (it is the same perturbation for every token and every step); the activation rounding is noise.
+# Two passes = single 16-bit activation x (weight hi + weight lo).
+def two_pass_study():
+    torch.set_num_threads(8)
+    sd = synth.make_state_dict(1234, live_only=True)
+    inp = synth.make_doc_inputs(0, H=192, W=256)
+    inp.pop("photo")
+    patch()
+    ref = run(sd, inp, {})
+    gg = ["pyramid", "embed", "dit", "decoder"]
+    attn = {"dit_attn": "fp16", "decoder_attn": "fp16"}
+    cases = [("all x3 (3 passes, shipping)", {**{g: "x3" for g in gg}, **attn}),
+             ("all: fp16 activation x weight pair (2 passes)", {**{g: "a16w3" for g in gg}, **attn}),
+             ("all: bf16 activation x weight pair (2 passes)", {**{g: "ab16w3" for g in gg}, **attn})]
+    cases += [(f"only {g}: fp16 activation x weight pair", {**{h: "x3" for h in gg}, g: "a16w3", **attn}) for g in gg]
+    print(f"{'case':52s} {'mean':>10s} {'max':>10s} {'mean px@4032':>13s} {'max px@4032':>12s}")
+    for name, modes in cases:
+        out = run(sd, inp, modes)
+        e = (out - ref).abs()
+        print(f"{name:52s} {float(e.mean()):10.3e} {float(e.max()):10.3e} {float(e.mean()) * 2015.5:13.4f} {float(e.max()) * 2015.5:12.4f}")
+        sys.stdout.flush()
+
+
+if __name__ == "__main__" and "--two-pass" in sys.argv:
+    two_pass_study()
+
+
+def decoder_breakdown():
+    """Which of the decoder's GEMMs tolerate a single fp16 activation operand (weights stay pairs)?"""
+    torch.set_num_threads(8)
+    sd = synth.make_state_dict(1234, live_only=True)
+    inp = synth.make_doc_inputs(0, H=192, W=256)
+    inp.pop("photo")
+    patch()
+    ref = run(sd, inp, {})
+    gg = ["pyramid", "embed", "dit", "decoder"]
+    x3 = {**{g: "x3" for g in gg}, "dit_attn": "fp16", "decoder_attn": "fp16"}
+    ids = {"qkv": {id(sd[f"decoder.layer_stack.{i}.attn.linear_{n}.weight"]) for i in range(6) for n in "qkv"},
+           "fc": {id(sd[f"decoder.layer_stack.{i}.attn.fc.weight"]) for i in range(6)},
+           "conv1": {id(sd[f"decoder.layer_stack.{i}.feed_forward.conv1.conv.weight"]) for i in range(6)},
+           "conv2": {id(sd[f"decoder.layer_stack.{i}.feed_forward.conv2.conv.weight"]) for i in range(6)}}
+    chosen = set()
+
+    def pick(x, w):
+        if id(w) in chosen:
+            return rnd(x, "fp16"), rnd(w, "x3")
+        m = Cfg.mode()
+        return rnd(x, amode(m)), rnd(w, wmode(m))
+
+    def linear(x, w, b=None):
+        a, ww = pick(x, w)
+        return TF.linear(a, ww, b)
+
+    def conv2d(x, w, b=None, **kw):
+        if kw.get("groups", 1) > 1:
+            return TF.conv2d(x, w, b, **kw)
+        a, ww = pick(x, w)
+        return TF.conv2d(a, ww, b, **kw)
+    O.F.linear, O.F.conv2d = linear, conv2d
+    print(f"{'decoder GEMMs with a single fp16 activation operand':52s} {'mean':>10s} {'max':>10s} {'mean px@4032':>13s} {'max px@4032':>12s}")
+    for names in (["qkv"], ["fc"], ["conv1"], ["conv2"], ["qkv", "conv1"], ["qkv", "conv1", "fc"]):
+        chosen.clear()
+        for n in names:
+            chosen.update(ids[n])
+        out = run(sd, inp, x3)
+        e = (out - ref).abs()
+        print(f"{'+'.join(names):52s} {float(e.mean()):10.3e} {float(e.max()):10.3e} {float(e.mean()) * 2015.5:13.4f} {float(e.max()) * 2015.5:12.4f}")
+        sys.stdout.flush()
+    chosen.clear()
+    chosen.update(ids["qkv"] | ids["conv1"])
+    out = run(sd, inp, {**x3, "pyramid": "a16w3", "embed": "a16w3", "dit": "a16w3"})
+    e = (out - ref).abs()
+    print(f"{'qkv+conv1 + pyramid, embeds and DiT block':52s} {float(e.mean()):10.3e} {float(e.max()):10.3e} {float(e.mean()) * 2015.5:13.4f} {float(e.max()) * 2015.5:12.4f}")
+
+
+if __name__ == "__main__" and "--decoder-breakdown" in sys.argv:
+    decoder_breakdown()

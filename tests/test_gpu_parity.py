@@ -267,6 +267,18 @@ def test_gemm_bf16x3_tcgen05(dev, M, N, K):
     assert err < 4e-5, err
 
 
+@pytest.mark.parametrize("M,N,K", [(2048, 4608, 1536), (256, 64, 64), (512, 384, 1032), (2048, 1536, 2048)])
+def test_gemm_fp16_activation_x_weight_pair(dev, M, N, K):
+    """Two-pass mode of the CTA-pair kernel (the decoder's q|k|v GEMM in bf16x3): ONE fp16 activation operand x weight hi + lo.
+    Exact against the fp16-rounded activation times the full weight."""
+    Cg, A, W, b = _run_gemm(dev, M, N, K, 3)
+    ref = (A.half().double() @ W.double().t() + b.double()).float()
+    err = float((Cg - ref).abs().max()) / max(1.0, float(ref.abs().max()))
+    assert err < 4e-5, err
+    full = (A.double() @ W.double().t() + b.double()).float()                        # and fp16-close to the unrounded product
+    assert float((Cg - full).abs().max()) / max(1.0, float(full.abs().max())) < 1e-3
+
+
 def test_gemm_bf16_more_row_tiles_than_grid_y(dev):
     """M / 128 > 65535 row tiles (the 512x512 pyramid levels of >= 32 documents in flight): the tile index is folded into
     gridDim.z, with a ragged last z-slice."""

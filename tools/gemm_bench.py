@@ -21,13 +21,14 @@ def main():
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tag = f"v1={os.environ.get('DVD_GEMM_V1','0')} bn={os.environ.get('DVD_GEMM_BN','auto')}"
-    modes = [m for m in ("bf16", "bf16x3") if ("--" + m) in sys.argv] or ["bf16", "bf16x3"]
+    modes = [m for m in ("bf16", "bf16x3", "a16w3") if ("--" + m) in sys.argv] or ["bf16", "bf16x3"]     # a16w3: fp16 A x fp16 weight pair (two passes)
     for mode in modes:
         for M, N, K, name in SHAPES:
             A = torch.randn(M, K, device=dev) * 0.5; W = torch.randn(N, K, device=dev) / K ** 0.5
-            Ah, Wh = A.bfloat16(), W.bfloat16()
+            wt = torch.float16 if mode == "a16w3" else torch.bfloat16          # a16w3: everything IEEE fp16
+            Ah, Wh = A.to(wt), W.to(wt)
             Al = (A - Ah.float()).bfloat16() if mode == "bf16x3" else None
-            Wl = (W - Wh.float()).bfloat16() if mode == "bf16x3" else None
+            Wl = (W - Wh.float()).to(wt) if mode != "bf16" else None
             b = torch.randn(N, device=dev); out = torch.empty(M, N, device=dev)
             st = _lib.stream_ptr()
 
@@ -64,6 +65,8 @@ def main():
             t = ts[len(ts) // 2]
             if mode == "bf16":
                 ref = Ah.double() @ Wh.double().t() + b.double()
+            elif mode == "a16w3":
+                ref = Ah.double() @ W.double().t() + b.double()
             else:
                 ref = A.double() @ W.double().t() + b.double()
             err = float((out.double() - ref).abs().max() / ref.abs().max())
