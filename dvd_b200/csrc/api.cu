@@ -155,3 +155,18 @@ extern "C" int dvd_gemm_bf16(const void* A16, const void* A16_lo, int lda, const
   w.hi = (const __nv_bfloat16*)W16; w.lo = (const __nv_bfloat16*)W16_lo; w.ld = ldw;
   return gemm_tc(a, w, M, N, K, e, (cudaStream_t)stream);
 }
+
+// Same with the epilogue pieces the decoder uses (tuning / micro-benchmarks): folded BN scale / shift, ReLU, a split-pair 16-bit output
+// (out16_lo) and an fp32 residual added in place of `out32` (resid may alias out32).
+extern "C" int dvd_gemm_tune(const void* A16, const void* A16_lo, int lda, const void* W16, const void* W16_lo, int ldw, const float* bias,
+                             const float* scale, const float* shift, int relu, void* out16, void* out16_lo, float* out32, const float* resid,
+                             int M, int N, int K, void* stream) {
+  Epilogue e; e.bias = bias; e.scale = scale; e.shift = shift; e.act = relu ? ACT_RELU : ACT_NONE;
+  e.out_bf16 = (__nv_bfloat16*)out16; e.out_lo = (__nv_bfloat16*)out16_lo; e.ldc_bf16 = N; e.out = out32; e.ldc = N;
+  e.resid = resid; e.ldr = N;
+  TcMat a, w;
+  a.hi = (const __nv_bfloat16*)A16; a.lo = (const __nv_bfloat16*)A16_lo; a.ld = lda;
+  a.f16 = !A16_lo && W16_lo;
+  w.hi = (const __nv_bfloat16*)W16; w.lo = (const __nv_bfloat16*)W16_lo; w.ld = ldw;
+  return gemm_tc(a, w, M, N, K, e, (cudaStream_t)stream);
+}

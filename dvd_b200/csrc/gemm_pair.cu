@@ -70,7 +70,8 @@ struct PairParams {
 #ifdef DVD_GEMM_TRACE
 __device__ unsigned long long g_pair_trace[512][16];
 __device__ __forceinline__ unsigned long long ptime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define PTRACE(slot) do { if ((slot) < 16) g_pair_trace[blockIdx.x & 511][slot] = ptime(); } while (0)
+__device__ int g_pair_trace_n;   // != 0: record only launches with this N (catches ONE GEMM of a whole step: tools/step_trace.py)
+#define PTRACE(slot) do { if ((slot) < 16 && (g_pair_trace_n == 0 || p.N == g_pair_trace_n)) g_pair_trace[blockIdx.x & 511][slot] = ptime(); } while (0)
 #else
 #define PTRACE(slot) do { } while (0)
 #endif
@@ -145,14 +146,32 @@ __device__ __forceinline__ void epi_load(const Epilogue& e, const EpiRowCtx& c, 
   }
 }
 
+// 4 x 4 transpose of 32-bit values inside a quad (lanes 4g .. 4g+3): lane q ends up with element q of every lane, in lane order.
+// The mma-fragment layout leaves a lane with 2 adjacent columns of a row (4 bytes of 16-bit output) per 8-column group; after the
+// transpose a lane holds 8 adjacent columns, so a 16-bit row segment leaves as ONE 16-byte store per lane and a quad covers 64
+// contiguous bytes (two full sectors) instead of four 4-byte stores per lane (16 bytes per quad: half sectors).  Measured inside a
+// step (tools/step_trace.py): the 4-byte stores of conv1's hi + lo tile took 8 us to drain the accumulator, 2.8 us in a bf16 microbench.
+__device__ __forceinline__ void quad_transpose4(uint32_t (&v)[4], int q) {
+  const bool b1 = (q & 2) != 0, b0 = (q & 1) != 0;
+  uint32_t s0 = b1 ? v[0] : v[2], s1 = b1 ? v[1] : v[3];
+  s0 = __shfl_xor_sync(0xffffffffu, s0, 2); s1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+  if (b1) { v[0] = s0; v[1] = s1; } else { v[2] = s0; v[3] = s1; }
+  uint32_t t0 = b0 ? v[0] : v[1], t1 = b0 ? v[2] : v[3];
+  t0 = __shfl_xor_sync(0xffffffffu, t0, 1); t1 = __shfl_xor_sync(0xffffffffu, t1, 1);
+  if (b0) { v[0] = t0; v[2] = t1; } else { v[1] = t0; v[3] = t1; }
+}
+
 template <int F, int O>
-__device__ __forceinline__ void epi_rows(const Epilogue& e, const Frag& f, const EpiRowCtx& c, int lane, const EpiLoads<F>& L, const LnRows& ln) {
-  const int tr = lane >> 2, tc2 = 2 * (lane & 3);
-  const int ld = (O == EO_F32 || O == EO_F32X) ? e.ldc : e.ldc_bf16;
+__device__ __forceinline__ void epi_rows(const Epilogue& e, const Frag& f, const EpiRowCtx& c, int lane, const EpiLoads<F>& L, const LnRows& ln,
+                                         const bool live) {                  // !live: instruction-cache warm-up pass, nothing is stored
+  const int tr = lane >> 2, q = lane & 3, tc2 = 2 * q;
+  constexpr bool OUT16 = (O != EO_F32);                       // a 16-bit tile is written (EO_F32X: next to the fp32 one)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const size_t o0 = (size_t)(c.orow0 + tr + 8 * i) * ld + c.col0 + tc2 + c.ocol_add;
+    const size_t orow = (size_t)(c.orow0 + tr + 8 * i);
+    const size_t o32 = orow * e.ldc + c.col0 + tc2 + c.ocol_add;
     float s1 = 0.f, s2 = 0.f;                                  // EO_F32X: this thread's share of the row's chunk statistics
+    uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float2 a = frag_val(f, i, j);
@@ -165,44 +184,33 @@ __device__ __forceinline__ void epi_rows(const Epilogue& e, const Frag& f, const
       if (F & EF_POS) { v0 += L.pv[i][j].x; v1 += L.pv[i][j].y; }
       if (F & EF_GATE) { v0 *= L.cg[j].x; v1 *= L.cg[j].y; }
       if (F & EF_RES) { v0 += L.qv[i][j].x; v1 += L.qv[i][j].y; }
-      const size_t off = o0 + 8 * j;
-      if (O == EO_F32X) {
-        *reinterpret_cast<float2*>(e.out + off) = make_float2(v0, v1);
-        const size_t off16 = (size_t)(c.orow0 + tr + 8 * i) * e.ldc_bf16 + c.col0 + tc2 + c.ocol_add + 8 * j;
-        if (e.out_lo) {
-          uint32_t hi, lo;
-          split_bf16x2(v0, v1, hi, lo);
-          *reinterpret_cast<uint32_t*>(e.out_bf16 + off16) = hi;
-          *reinterpret_cast<uint32_t*>(e.out_lo + off16) = lo;
-        } else {
-          *reinterpret_cast<uint32_t*>(e.out_bf16 + off16) = pack_bf16x2(v0, v1);
-        }
-        s1 += v0 + v1; s2 += v0 * v0 + v1 * v1;
-      } else if (O == EO_F32) {
-        *reinterpret_cast<float2*>(e.out + off) = make_float2(v0, v1);
-      } else if (O == EO_PAIR) {
-        uint32_t hi, lo;
-        split_bf16x2(v0, v1, hi, lo);
-        *reinterpret_cast<uint32_t*>(e.out_bf16 + off) = hi;
-        *reinterpret_cast<uint32_t*>(e.out_lo + off) = lo;
-      } else if (O == EO_F16) {
-        *reinterpret_cast<uint32_t*>(e.out_bf16 + off) = pack_f16x2(v0, v1);
-      } else {
-        *reinterpret_cast<uint32_t*>(e.out_bf16 + off) = pack_bf16x2(v0, v1);
+      if ((O == EO_F32 || O == EO_F32X) && live) *reinterpret_cast<float2*>(e.out + o32 + 8 * j) = make_float2(v0, v1);
+      if (O == EO_F32X) { s1 += v0 + v1; s2 += v0 * v0 + v1 * v1; }
+      if (O == EO_PAIR || (O == EO_F32X && e.out_lo)) split_bf16x2(v0, v1, hi[j], lo[j]);
+      else if (O == EO_F16) hi[j] = pack_f16x2(v0, v1);
+      else if (OUT16) hi[j] = pack_bf16x2(v0, v1);
+    }
+    if (OUT16) {
+      const size_t o16 = orow * e.ldc_bf16 + c.col0 + c.ocol_add + 8 * q;     // this lane's 8 columns after the transpose
+      quad_transpose4(hi, q);
+      if (live) *reinterpret_cast<uint4*>(e.out_bf16 + o16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (O == EO_PAIR || (O == EO_F32X && e.out_lo)) {
+        quad_transpose4(lo, q);
+        if (live) *reinterpret_cast<uint4*>(e.out_lo + o16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
     if (O == EO_F32X) {
       // the quad holds the 32 columns of this chunk of row tr + 8i: fixed-order butterfly, then one (sum, sum of squares) per chunk
       s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
       s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-      if ((lane & 3) == 0)
+      if (q == 0 && live)
         *reinterpret_cast<float2*>(e.stats_out + ((size_t)(c.orow0 + tr + 8 * i) * (c.N >> 5) + ((c.col0 + c.ocol_add) >> 5)) * 2) = make_float2(s1, s2);
     }
   }
 }
 
 // any other Epilogue: run-time options (kept out of line: it is not on the denoiser's path)
-__device__ __noinline__ void epi_rows_generic(const Epilogue& e, const Frag& f, const EpiRowCtx& c, int lane) {
+__device__ __noinline__ void epi_rows_generic(const Epilogue& e, const Frag& f, const EpiRowCtx& c, int lane, const bool live) {
   const int tr = lane >> 2, tc2 = 2 * (lane & 3);
 #pragma unroll 1
   for (int ij = 0; ij < 16; ++ij) {
@@ -226,6 +234,7 @@ __device__ __noinline__ void epi_rows_generic(const Epilogue& e, const Frag& f, 
       v[k] = x;
     }
     const int orow = c.orow0 + rr, ocol = col + c.ocol_add;
+    if (!live) continue;
     if (e.out) *reinterpret_cast<float2*>(e.out + (size_t)orow * e.ldc + ocol) = make_float2(v[0], v[1]);
     if (e.out_bf16) {
       const size_t off = (size_t)orow * e.ldc_bf16 + ocol;
@@ -334,23 +343,32 @@ __device__ __forceinline__ void epilogue_loop(const PairParams& p, const Epilogu
         ln.rs[i] = __shfl_sync(0xffffffffu, rstd, (lane >> 2) + 8 * i);
       }
     }
-    mbar_wait(&acc_full[buf], (it >> 1) & 1);
-    if (warp == PP_EPI_WARP0 && lane == 0 && it < 2) PTRACE(4 + 5 * it);          // accumulator complete
-    fence_after_sync();
     const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (BN / 2));
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
+    // The chunk body is ONE copy of code run NCH times (not unrolled), and the pair's first unit runs it once more up front as a
+    // dry pass (pass -1: garbage accumulator, stores predicated off) while the main loop is still busy.  A launch executes an
+    // epilogue body it has not run for ~100 us; the instruction fetch of the cold, straight-line code took 3.3 us per chunk inside a
+    // step against 0.6 us in a back-to-back micro-benchmark (tools/step_trace.py: conv1's 4 chunks 14 us vs 2.8 us) - the dry pass
+    // pulls the body into the instruction caches for free.
+#pragma unroll 1
+    for (int pass = (it == 0 ? -1 : 0); pass < NCH; ++pass) {
+      const bool live = pass >= 0;
+      const int ch = live ? pass : 0;
+      if (pass == 0) {
+        mbar_wait(&acc_full[buf], (it >> 1) & 1);
+        if (warp == PP_EPI_WARP0 && lane == 0 && it < 2) PTRACE(4 + 5 * it);          // accumulator complete
+        fence_after_sync();
+      }
       rc.col0 = q.n0 + half * (BN / 2) + ch * 32;
       Frag f;
       tmem_ld_16x256b_x4(tacc + (uint32_t)(ch * 32), f.a);
       tmem_ld_16x256b_x4(tacc + (16u << 16) + (uint32_t)(ch * 32), f.b);
-      if (F >= 0 && ch + 1 < NCH) {                           // next chunk's operands
+      if (F >= 0 && live && ch + 1 < NCH) {                   // next chunk's operands
         EpiRowCtx rn = rc; rn.col0 = rc.col0 + 32;
         epi_load<FF>(e, rn, lane, nxt);
       }
       tmem_ld_wait();
-      if (warp == PP_EPI_WARP0 && lane == 0 && it == 0 && ch == 0) PTRACE(7);
-      if (ch == NCH - 1) {                                    // accumulator fully copied out: hand the buffer back to the MMA warp
+      if (live && warp == PP_EPI_WARP0 && lane == 0 && it == 0 && ch == 0) PTRACE(7);
+      if (live && ch == NCH - 1) {                            // accumulator fully copied out: hand the buffer back to the MMA warp
         if (warp == PP_EPI_WARP0 && lane == 0 && it < 2) PTRACE(5 + 5 * it);      // TMEM drained
         fence_before_sync();
         __syncwarp();
@@ -374,15 +392,17 @@ __device__ __forceinline__ void epilogue_loop(const PairParams& p, const Epilogu
             float2 a = frag_val(f, i, j);
             if (FF & EF_LN) { a.x = ln.rs[i] * (a.x - ln.m[i] * c2.x); a.y = ln.rs[i] * (a.y - ln.m[i] * c2.y); }
             uint16_t* o = vt + ((size_t)(row >> 10) * (p.N - e.vt_col0) + (col - e.vt_col0)) * 1024 + (row & 1023);
-            o[0] = cvt16(a.x + b2.x, e.out_f16);
-            o[1024] = cvt16(a.y + b2.y, e.out_f16);
+            if (live) {
+              o[0] = cvt16(a.x + b2.x, e.out_f16);
+              o[1024] = cvt16(a.y + b2.y, e.out_f16);
+            }
           }
         }
       }
-      if (F >= 0) epi_rows<FF, O>(e, f, rc, lane, cur, ln);
-      else epi_rows_generic(e, f, rc, lane);
-      if (warp == PP_EPI_WARP0 && lane == 0 && it == 0 && ch == 0) PTRACE(11);
-      if (F >= 0 && ch + 1 < NCH) cur = nxt;
+      if (F >= 0) epi_rows<FF, O>(e, f, rc, lane, cur, ln, live);
+      else epi_rows_generic(e, f, rc, lane, live);
+      if (live && warp == PP_EPI_WARP0 && lane == 0 && it == 0 && ch == 0) PTRACE(11);
+      if (F >= 0 && live && ch + 1 < NCH) cur = nxt;
     }
     if (warp == PP_EPI_WARP0 && lane == 0 && it < 2) PTRACE(6 + 5 * it);          // epilogue of the unit done (this warp)
   }
@@ -686,6 +706,9 @@ int gemm_pair_dispatch(const TcMat& A, const TcMat& W, int M, int N, int K, cons
               "gemm_pair: fused LN needs ln_colsum and an even number of 32-column chunks");
   DVD_REQUIRE(!e.stats_out || (N % 32 == 0 && !e.group_rows), "gemm_pair: row statistics need N %% 32 == 0 and no stream remap");
   DVD_REQUIRE(!conv || (conv_w % 128 == 0 && conv_cin % 64 == 0 && K == 9 * conv_cin), "gemm_pair: bad conv geometry");
+  DVD_REQUIRE(!e.out_bf16 || (e.ldc_bf16 % 8 == 0 && e.group_col_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(e.out_bf16) & 15) == 0 &&
+                              (reinterpret_cast<uintptr_t>(e.out_lo) & 15) == 0),
+              "gemm_pair: 16-bit outputs are stored 16 bytes at a time (ld %% 8, 16-byte aligned bases)");
   const int bn = pick_bn(M, N, K, mode, sm_count() / 2);
   if (conv) return mode ? launch_pair_bn<1, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st)
                         : launch_pair_bn<0, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
@@ -697,6 +720,9 @@ int gemm_pair_dispatch(const TcMat& A, const TcMat& W, int M, int N, int K, cons
 }  // namespace dvd
 
 #ifdef DVD_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int dvd_debug_pair_trace_filter(int n) {
+  return (int)cudaMemcpyToSymbol(dvd::g_pair_trace_n, &n, sizeof(int));
+}
 extern "C" __attribute__((visibility("default"))) int dvd_debug_pair_trace(unsigned long long* out, int n_ctas) {
   return (int)cudaMemcpyFromSymbol(out, dvd::g_pair_trace, (size_t)n_ctas * 16 * sizeof(unsigned long long));
 }

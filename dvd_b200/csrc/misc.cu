@@ -613,8 +613,8 @@ __global__ void __launch_bounds__(256) k_dwconv(const float4* __restrict__ in, c
 // ahead of griddepcontrol.wait); a thread walks the strip column by column (kx outer): 3 weight rows (ky) in registers, every input
 // row of the strip loaded once and fed to up to three output rows -> (RS+2)*3 activation loads + 18 LDS.128 per RS outputs, ~80
 // registers, one wave of 512 CTAs.
-template <int RS>
-__global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ in, const uint4* __restrict__ in_lo, const float* __restrict__ w9,
+template <int RS, int NW>
+__global__ void __launch_bounds__(32 * NW) k_dwconv_bf16(const uint4* __restrict__ in, const uint4* __restrict__ in_lo, const float* __restrict__ w9,
                                                      const float* __restrict__ sc, const float* __restrict__ sh, uint4* __restrict__ out,
                                                      uint4* __restrict__ out_lo, int C8) {
   __shared__ __align__(16) float s_w[9][256];
@@ -622,14 +622,16 @@ __global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ i
   pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c8 = blockIdx.x * 32 + lane;                  // 8-channel group of this thread
-  const int x = blockIdx.y * 8 + warp;
+  const int x = blockIdx.y * NW + warp;
   const int strips = 32 / RS;
   const size_t n = blockIdx.z / strips;
   const int y0 = (blockIdx.z % strips) * RS;
   const int C = C8 * 8, cb = blockIdx.x * 256;            // first channel of the CTA
-  for (int e = threadIdx.x; e < 9 * 256; e += 256) s_w[e >> 8][e & 255] = (cb + (e & 255) < C) ? __ldg(w9 + (size_t)(e >> 8) * C + cb + (e & 255)) : 0.f;
-  s_sc[threadIdx.x] = (cb + threadIdx.x < C) ? __ldg(sc + cb + threadIdx.x) : 0.f;
-  s_sh[threadIdx.x] = (cb + threadIdx.x < C) ? __ldg(sh + cb + threadIdx.x) : 0.f;
+  for (int e = threadIdx.x; e < 9 * 256; e += 32 * NW) s_w[e >> 8][e & 255] = (cb + (e & 255) < C) ? __ldg(w9 + (size_t)(e >> 8) * C + cb + (e & 255)) : 0.f;
+  for (int e = threadIdx.x; e < 256; e += 32 * NW) {
+    s_sc[e] = (cb + e < C) ? __ldg(sc + cb + e) : 0.f;
+    s_sh[e] = (cb + e < C) ? __ldg(sh + cb + e) : 0.f;
+  }
   __syncthreads();
   pdl_wait();
   if (c8 >= C8) return;
@@ -689,9 +691,11 @@ __global__ void __launch_bounds__(256) k_dwconv_bf16(const uint4* __restrict__ i
 int dwconv3x3_bn_relu_bf16(const __nv_bfloat16* in, const __nv_bfloat16* in_lo, const float* w9c, const float* scale, const float* shift,
                            __nv_bfloat16* out, __nv_bfloat16* out_lo, int N, int C, cudaStream_t st) {
   DVD_REQUIRE(in && w9c && scale && shift && out && C % 8 == 0, "dwconv_bf16: bad args");
-  constexpr int RS = 4;
+  // 4 warps (4 columns) per CTA: at ~93 registers a 256-thread CTA fits twice per SM, and the 512 CTAs of one document then run as
+  // 1.7 waves of 296; the 1024 CTAs of 128 threads (5 per SM) backfill much more evenly.
+  constexpr int RS = 4, NW = 4;
   DVD_REQUIRE((long long)N * (32 / RS) <= 65535, "dwconv_bf16: batch too large for the grid");
-  DVD_CUDA(launch_pdl(8, k_dwconv_bf16<RS>, dim3(cdiv(C / 8, 32), 4, N * (32 / RS)), dim3(256), (size_t)0, st, (const uint4*)in, (const uint4*)in_lo, w9c, scale,
+  DVD_CUDA(launch_pdl(8, k_dwconv_bf16<RS, NW>, dim3(cdiv(C / 8, 32), 32 / NW, N * (32 / RS)), dim3(32 * NW), (size_t)0, st, (const uint4*)in, (const uint4*)in_lo, w9c, scale,
                       shift, (uint4*)out, (uint4*)out_lo, C / 8));
   DVD_LAUNCH_CHECK("k_dwconv_bf16");
   return 0;

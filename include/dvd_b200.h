@@ -198,6 +198,11 @@ DVD_API int dvd_test_attention(const float* q, const float* k, const float* v, f
  * dvd_test_gemm accepts precision 3 for the same two-pass mode (fp16 activation x fp16 weight pair). */
 DVD_API int dvd_gemm_bf16(const void* A16, const void* A16_lo, int lda, const void* W16, const void* W16_lo, int ldw,
                           const float* bias, void* out16, float* out32, int M, int N, int K, void* stream);
+/* Same with the decoder's epilogue pieces: folded-BN scale / shift (NULL: none), ReLU, a split-pair 16-bit output (out16_lo) and an
+ * fp32 residual (resid may alias out32). */
+DVD_API int dvd_gemm_tune(const void* A16, const void* A16_lo, int lda, const void* W16, const void* W16_lo, int ldw,
+                          const float* bias, const float* scale, const float* shift, int relu, void* out16, void* out16_lo,
+                          float* out32, const float* resid, int M, int N, int K, void* stream);
 /* Kernel-class profiler: between begin/end every dense contraction launched by this thread is bracketed by CUDA
  * events.  end() synchronises and returns, for the classes {0: GEMM, 1: attention, 2: pyramid conv}, the summed
  * device time (ms), algorithmic FLOPs (2 M N K), launch counts and the FLOPs the tensor pipe executed (the split-precision

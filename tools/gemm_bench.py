@@ -4,6 +4,7 @@ Usage: python tools/gemm_bench.py [--check] [--graph]
   --graph : 16 launches captured in ONE CUDA graph over rotating weight / output buffers (> L2 in total), replayed: the time per
             launch a step of the pipeline sees (no host time between kernels)
   --check : fewer runs (used by the parity tests)
+  --epi=conv1|conv2 : (with --graph) the decoder's epilogues instead of bias + bf16: BN scale/shift + ReLU -> bf16 pair; BN + ReLU + fp32 residual
 env: DVD_GEMM_V1=1 selects the generic single-CTA kernel; DVD_GEMM_BN forces the tile width of the persistent CTA-pair kernel; DVD_GEMM_DEBUG=1 prints the chosen configuration per launch."""
 import os, sys
 import torch
@@ -32,7 +33,16 @@ def main():
             b = torch.randn(N, device=dev); out = torch.empty(M, N, device=dev)
             st = _lib.stream_ptr()
 
-            def run(Wh_=Wh, Wl_=Wl, out16=None, out32=out):
+            epi = ([a.split("=")[1] for a in sys.argv if a.startswith("--epi=")] or [""])[0]
+            sc, sh = torch.rand(N, device=dev) + 0.5, torch.randn(N, device=dev)
+
+            def run(Wh_=Wh, Wl_=Wl, out16=None, out32=out, out_lo=None, res=None):
+                if epi == "conv1" and out16 is not None:
+                    return _lib.check(lib.dvd_gemm_tune(_lib.ptr(Ah), _lib.ptr(Al), K, _lib.ptr(Wh_), _lib.ptr(Wl_), K, None, _lib.ptr(sc), _lib.ptr(sh), 1,
+                                                        _lib.ptr(out16), _lib.ptr(out_lo), None, None, M, N, K, _lib.stream_ptr()), "gemm")
+                if epi == "conv2" and res is not None:
+                    return _lib.check(lib.dvd_gemm_tune(_lib.ptr(Ah), _lib.ptr(Al), K, _lib.ptr(Wh_), _lib.ptr(Wl_), K, None, _lib.ptr(sc), _lib.ptr(sh), 1,
+                                                        None, None, _lib.ptr(res), _lib.ptr(res), M, N, K, _lib.stream_ptr()), "gemm")
                 _lib.check(lib.dvd_gemm_bf16(_lib.ptr(Ah), _lib.ptr(Al), K, _lib.ptr(Wh_), _lib.ptr(Wl_), K, _lib.ptr(b), _lib.ptr(out16), _lib.ptr(out32),
                                              M, N, K, _lib.stream_ptr()), "gemm")
             for _ in range(2 if check else 3):
@@ -42,11 +52,14 @@ def main():
                 # bf16 output like the pipeline's GEMMs; 8 weight copies (8 x 14 MB for the QKV shape) so that weights stream from HBM
                 R = 16
                 Ws = [(Wh.clone(), Wl.clone() if Wl is not None else None) for _ in range(8)]
-                outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(4)]
+                nout = 16 if epi else 4                       # --epi: 16 cold output sets (> L2 together with the weights)
+                outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(nout)]
+                los = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(nout)] if epi == "conv1" else [None] * nout
+                ress = [torch.zeros(M, N, device=dev) for _ in range(nout)] if epi == "conv2" else [None] * nout
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     for i in range(R):
-                        run(Ws[i % 8][0], Ws[i % 8][1], outs[i % 4], None)
+                        run(Ws[i % 8][0], Ws[i % 8][1], outs[i % nout], None, los[i % nout], ress[i % nout])
                 g.replay(); torch.cuda.synchronize()
                 ts = []
                 for i in range(5):
