@@ -230,9 +230,14 @@ k_attn_pair(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
       l = l * alpha + (sum0 + sum1);
       if (tr) ATRACE(t, 5);
-      if (t > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {       // identical decision in both warps of the pair (same rows, same m)
+      if (t > 0) {
+        // Every phase of pv_done is waited for, in order, by every softmax thread (P V(t-1) was issued a whole softmax step ago, so this
+        // does not stall): a parity wait may lag ONE phase at most, and the final wait below would otherwise be able to mistake the
+        // completion of P V(nt-3) for that of P V(nt-1).
         mbar_wait(pv_done, (t - 1) & 1);                           // P V(t-1) finished: O readable
         fence_after_sync();
+      }
+      if (t > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {       // identical decision in both warps of the pair (same rows, same m)
 #pragma unroll 1
         for (int c = half * (PD / 2); c < (half + 1) * (PD / 2); c += 32) {
           uint32_t o[32];
@@ -298,7 +303,8 @@ k_attn_pair(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 }
 
 bool attention_pair_supported(int T, int d, int nctx) {
-  static const int off = getenv("DVD_ATTN_V1") ? atoi(getenv("DVD_ATTN_V1")) : 0;
+  const char* v1 = getenv("DVD_ATTN_V1");                           // (read per call: tests switch kernels inside one process)
+  const int off = v1 ? atoi(v1) : 0;
   return !off && d == PD && nctx == 1 && T % (2 * PQ) == 0 && T % PKV == 0;
 }
 

@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(32 * NW) k_dwconv_bf16(const uint4* __restrict
   for (int o = 0; o < RS; ++o)
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[o][k] = 0.f;
-#pragma unroll
+#pragma unroll 1                                             // (one copy of the column body: the kernel's code is fetched cold on every launch)
   for (int kx = 0; kx < 3; ++kx) {
     const int xx = x + kx - 1;
     if (xx < 0 || xx >= 32) continue;

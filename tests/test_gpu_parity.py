@@ -332,6 +332,16 @@ def test_attention_fp16_tcgen05(dev, d):
     assert float((o - ref).abs().max()) < 3e-3 and float((o - ref).abs().mean()) < 2.5e-4
 
 
+def test_attention_d256_single_cta_fallback(dev, monkeypatch):
+    """DVD_ATTN_V1=1: the decoder attention on the single-CTA kernel (the path for T not a multiple of 256) gives the same result
+    as the CTA-pair kernel to fp16 accuracy."""
+    o_pair, q, k, v = _run_attn(dev, 2, 6, 1024, 256, 2)
+    monkeypatch.setenv("DVD_ATTN_V1", "1")
+    o_v1, _, _, _ = _run_attn(dev, 2, 6, 1024, 256, 2)
+    ref = O._mha_core(q.half().float(), k.half().float(), v.half().float(), 6, 256 ** -0.5)
+    assert float((o_v1 - ref).abs().max()) < 3e-3 and float((o_pair - o_v1).abs().max()) < 3e-3
+
+
 # ----------------------------------------------------------------------------------------------- denoiser stages
 def test_static_forward_and_first_step_fp32(dev, models, state_dict_live, golden_dir):
     sd, model = state_dict_live, models["fp32"]

@@ -184,3 +184,20 @@ def test_committed_bench_lines_carry_the_contract():
         assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert n >= 5
+
+
+def test_split_f16_pair_reconstructs_weights():
+    """weights.split_f16: hi + lo reproduces an fp32 weight to ~2^-22 relative (the fp16 pair of the two-pass q|k|v GEMM)."""
+    import torch
+    from dvd_b200.weights import split_f16, split_bf16
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(256, 384, generator=g) * 0.05
+    hi, lo = split_f16(w)
+    assert hi.dtype == torch.float16 and lo.dtype == torch.float16
+    err = (hi.float() + lo.float() - w).abs().max() / w.abs().max()
+    assert float(err) < 2e-6
+    bh, bl = split_bf16(w)
+    assert float((bh.float() + bl.float() - w).abs().max() / w.abs().max()) < 2e-5
+    import pytest
+    with pytest.raises(ValueError):
+        split_f16(torch.full((2, 2), 1e5))
