@@ -40,7 +40,7 @@ class Weights(C.Structure):
                 ("h_scale0", Mat), ("h_scale2", Mat), ("w_scale0", Mat), ("w_scale2", Mat),
                 ("h_scale0_b", _vp), ("h_scale2_b", _vp), ("w_scale0_b", _vp), ("w_scale2_b", _vp),
                 ("dec", DecLayer * 6), ("dec_ln_w", _vp), ("dec_ln_b", _vp), ("fin", Mat), ("fin_b", _vp),
-                ("fin_ada", Mat), ("fin_ada_b", _vp)]
+                ("fin_ada", Mat), ("fin_ada_b", _vp), ("pyr_h", Mat * 7)]
 
 
 # name -> (restype, argtypes); mirrors include/dvd_b200.h one to one

@@ -1,6 +1,7 @@
 // Persistent CTA-pair tcgen05 GEMM: the kernel every dense layer of the denoiser runs on.
 //
-//   C[M,N] = epilogue(A[M,K] * W[N,K]^T)      A, W K-major 16-bit (bf16, or bf16 hi + lo pairs = 3 tensor-core passes, DVD_PREC_BF16X3)
+//   C[M,N] = epilogue(A[M,K] * W[N,K]^T)      A, W K-major 16-bit: bf16 (1 tensor-core pass), bf16 hi + lo pairs on both sides (3 passes,
+//                                             DVD_PREC_BF16X3), or ONE fp16 activation x fp16 weight pair (2 passes: the decoder's q|k|v GEMM)
 //
 // Shape of the machine: 74 clusters of two CTAs (the two SMs of a TPC), one cluster per TPC, each looping over work units.
 //   * a unit = one 256 x BN output tile (UMMA M = 256 across the pair, tcgen05.mma.cta_group::2); units are dealt round-robin
@@ -12,11 +13,13 @@
 //     k-block of a 128 x 256 tile, which is what bounds a one-SM-per-tile kernel (~13 TB/s of L2 reads at 1.1 PFLOP/s).
 //   * warp 0 (one lane, both CTAs)  TMA producer: ring of 3..8 stages of [A_hi | A_lo | W_hi | W_lo] boxes (SWIZZLE_128B), continuous
 //     across units; transaction bytes of both CTAs are counted on the LEADER's full barrier.
-//   * warp 1 (one lane, leader)     MMA issuer: 4 (or 12: hi*hi, lo*hi, hi*lo) UMMA 256 x BN x 16 per stage into one of TWO TMEM
-//     accumulators; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs.
+//   * warp 1 (leader; the whole warp runs the loop, one ELECTED lane issues)  MMA issuer: 4 / 12 / 8 UMMA 256 x BN x 16 per stage into one
+//     of TWO TMEM accumulators; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs.
 //   * warps 4..11 (both CTAs)       epilogue of the CTA's own 128 rows, overlapping the next unit's main loop: each warp owns a TMEM
 //     lane quarter x half of the columns; tcgen05.ld 16x256b (mma-fragment layout: a quad holds one 32-byte sector of a row) -> fused
-//     epilogue in registers -> sector-complete global accesses, no shared-memory staging.
+//     epilogue in registers -> sector-complete global accesses, no shared-memory staging (16-bit rows: 4 x 4 quad transpose -> 16-byte
+//     stores).  The 32-column chunk body is ONE rolled copy of code, warmed by a dry pass while the first main loop runs (cold
+//     instruction fetch was 3.3 us per chunk inside a step).
 //   * CONV: A is an NHWC activation read through a 4-D tensor map (implicit GEMM of the 3x3 pyramid convolutions, zero padding = TMA
 //     out-of-bounds fill); a pair covers 256 consecutive pixels of one image row.
 #include "gemm_tc.cuh"
@@ -275,7 +278,7 @@ static int classify_epilogue(const Epilogue& e) {
     case epi_key(EF_RES, EO_F32): case epi_key(EF_GATE | EF_RES, EO_F32):
     case epi_key(EF_GELU, EO_BF16): case epi_key(EF_GELUX, EO_PAIR):
     case epi_key(EF_SCALE | EF_FLOOR, EO_BF16): case epi_key(EF_SCALE | EF_FLOOR, EO_PAIR): case epi_key(EF_SCALE | EF_FLOOR | EF_RES, EO_F32):
-    case epi_key(EF_FLOOR, EO_BF16): case epi_key(EF_FLOOR, EO_PAIR):
+    case epi_key(EF_FLOOR, EO_BF16): case epi_key(EF_FLOOR, EO_PAIR): case epi_key(EF_FLOOR, EO_F16):
     case epi_key(EF_LN, EO_F16): case epi_key(EF_LN, EO_BF16):
     case epi_key(EF_LN | EF_SCALE | EF_FLOOR, EO_PAIR): case epi_key(EF_LN | EF_SCALE | EF_FLOOR, EO_BF16):
     case epi_key(EF_RES, EO_F32X): case epi_key(EF_SCALE | EF_FLOOR | EF_RES, EO_F32X):
@@ -457,7 +460,7 @@ k_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       DVD_EPI_CASE(EF_RES, EO_F32) DVD_EPI_CASE(EF_GATE | EF_RES, EO_F32)
       DVD_EPI_CASE(EF_GELU, EO_BF16) DVD_EPI_CASE(EF_GELUX, EO_PAIR)
       DVD_EPI_CASE(EF_SCALE | EF_FLOOR, EO_BF16) DVD_EPI_CASE(EF_SCALE | EF_FLOOR, EO_PAIR) DVD_EPI_CASE(EF_SCALE | EF_FLOOR | EF_RES, EO_F32)
-      DVD_EPI_CASE(EF_FLOOR, EO_BF16) DVD_EPI_CASE(EF_FLOOR, EO_PAIR)
+      DVD_EPI_CASE(EF_FLOOR, EO_BF16) DVD_EPI_CASE(EF_FLOOR, EO_PAIR) DVD_EPI_CASE(EF_FLOOR, EO_F16)
       DVD_EPI_CASE(EF_LN, EO_F16) DVD_EPI_CASE(EF_LN, EO_BF16)
       DVD_EPI_CASE(EF_LN | EF_SCALE | EF_FLOOR, EO_PAIR) DVD_EPI_CASE(EF_LN | EF_SCALE | EF_FLOOR, EO_BF16)
       DVD_EPI_CASE(EF_RES, EO_F32X) DVD_EPI_CASE(EF_SCALE | EF_FLOOR | EF_RES, EO_F32X)
@@ -698,7 +701,6 @@ int gemm_pair_dispatch(const TcMat& A, const TcMat& W, int M, int N, int K, cons
   const bool conv = conv_h > 0;
   const int mode = A.lo ? 1 : (A.f16 ? 2 : 0);
   DVD_REQUIRE(mode == 0 || W.lo, "gemm_pair: the weight's low half is missing");
-  DVD_REQUIRE(mode != 2 || !conv, "gemm_pair: the fp16-activation mode has no implicit-GEMM instantiation");
   DVD_REQUIRE(gemm_pair_supported(M, N, K, conv), "gemm_pair: unsupported shape M=%d N=%d K=%d", M, N, K);
   DVD_REQUIRE(epilogue_periods_ok(e), "gemm_pair: resid_mod / pos_rows / group_rows must be multiples of 128");
   DVD_REQUIRE((!e.ln_stats && !e.stats_out) || classify_epilogue(e) != EPI_GENERIC, "gemm_pair: fused-LN / row-statistics epilogue combination not compiled");
@@ -710,6 +712,7 @@ int gemm_pair_dispatch(const TcMat& A, const TcMat& W, int M, int N, int K, cons
                               (reinterpret_cast<uintptr_t>(e.out_lo) & 15) == 0),
               "gemm_pair: 16-bit outputs are stored 16 bytes at a time (ld %% 8, 16-byte aligned bases)");
   const int bn = pick_bn(M, N, K, mode, sm_count() / 2);
+  if (conv && mode == 2) return launch_pair_bn<2, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
   if (conv) return mode ? launch_pair_bn<1, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st)
                         : launch_pair_bn<0, true>(bn, A, W, M, N, K, e, conv_b, conv_h, conv_w, conv_cin, st);
   if (mode == 2) return launch_pair_bn<2, false>(bn, A, W, M, N, K, e, 0, 0, 0, 0, st);

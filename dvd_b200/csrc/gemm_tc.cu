@@ -389,13 +389,15 @@ int gemm_tc(const TcMat& A, const TcMat& W, int M, int N, int K, const Epilogue&
 int conv3x3_tc(const TcMat& in, const TcMat& Wt, int B, int H, int Wd, int Cin, int Cout, const Epilogue& e, cudaStream_t st) {
   DVD_REQUIRE(in.hi && Wt.hi && (e.out || e.out_bf16), "conv3x3_tc: null pointer");
   DVD_REQUIRE(Cin % 64 == 0 && Wd % 128 == 0 && (Cout == 64 || Cout % 128 == 0), "conv3x3_tc: unsupported shape Cin=%d W=%d Cout=%d", Cin, Wd, Cout);
-  DVD_REQUIRE((in.lo != nullptr) == (Wt.lo != nullptr), "conv3x3_tc: activation and weight must both be split pairs or both plain");
+  DVD_REQUIRE(in.f16 ? (!in.lo && Wt.lo) : ((in.lo != nullptr) == (Wt.lo != nullptr)),
+              "conv3x3_tc: activation and weight must both be split pairs or both plain (or: fp16 activation with an fp16 weight pair)");
   const int M = B * H * Wd, K = 9 * Cin;
   int rc = check_epilogue(e, Cout); if (rc) return rc;
   if (!use_v1() && gemm_pair_supported(M, Cout, K, true)) {
     TcMat w = Wt; w.ld = K;
     return gemm_pair_dispatch(in, w, M, Cout, K, e, B, H, Wd, Cin, st);
   }
+  DVD_REQUIRE(!in.f16, "conv3x3_tc: the fp16-activation mode needs the CTA-pair kernel");
   const bool x3 = in.lo != nullptr;
   const int bn = Cout == 64 ? 64 : ((Cout % 256 == 0 && (long long)(M / 128) * (Cout / 256) >= 2LL * sm_count()) ? 256 : 128);
   CUtensorMap tmA, tmB, tmAl, tmBl;

@@ -109,7 +109,7 @@ int maxpool2_nhwc(const float* in, float* out, int B, int H, int W, int C, cudaS
 // one thread = one (pixel, tap pair): 8 of the 16-byte chunks of a 128-byte output row; chunks 5..7 (k >= 40) are zero and
 // chunk 4 holds tap 8 + zeros
 __global__ void __launch_bounds__(256) k_im2col_c4(const float4* __restrict__ in, uint4* __restrict__ out, uint4* __restrict__ out_lo, int H, int W,
-                                                   size_t total) {
+                                                   size_t total, int f16) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // total = B*H*W*8 chunks
   if (i >= total) return;
   const int chunk = i & 7; const size_t pix = i >> 3;
@@ -125,15 +125,20 @@ __global__ void __launch_bounds__(256) k_im2col_c4(const float4* __restrict__ in
     }
   }
   uint4 o, l;
+  if (f16) {                                   // one IEEE fp16 value per element (two-pass mode of the pyramid)
+    o = make_uint4(pack_f16x2(v[0].x, v[0].y), pack_f16x2(v[0].z, v[0].w), pack_f16x2(v[1].x, v[1].y), pack_f16x2(v[1].z, v[1].w));
+    out[i] = o;
+    return;
+  }
   split_bf16x2(v[0].x, v[0].y, o.x, l.x); split_bf16x2(v[0].z, v[0].w, o.y, l.y);
   split_bf16x2(v[1].x, v[1].y, o.z, l.z); split_bf16x2(v[1].z, v[1].w, o.w, l.w);
   out[i] = o;
   if (out_lo) out_lo[i] = l;
 }
-int im2col3x3_c4_bf16(const float* in, __nv_bfloat16* out, __nv_bfloat16* out_lo, int B, int H, int W, cudaStream_t st) {
+int im2col3x3_c4_bf16(const float* in, __nv_bfloat16* out, __nv_bfloat16* out_lo, int B, int H, int W, cudaStream_t st, int out_f16) {
   DVD_REQUIRE(in && out && B > 0, "im2col: bad args");
   size_t total = (size_t)B * H * W * 8;
-  k_im2col_c4<<<cdiv(total, 256), 256, 0, st>>>((const float4*)in, (uint4*)out, (uint4*)out_lo, H, W, total);
+  k_im2col_c4<<<cdiv(total, 256), 256, 0, st>>>((const float4*)in, (uint4*)out, (uint4*)out_lo, H, W, total, out_f16);
   DVD_LAUNCH_CHECK("k_im2col_c4");
   return 0;
 }
@@ -141,7 +146,7 @@ int im2col3x3_c4_bf16(const float* in, __nv_bfloat16* out, __nv_bfloat16* out_lo
 // 2x2 max pool on bf16 NHWC (8 channels = 16 bytes per thread); the input may be a split pair (value = hi + lo), the output is
 // written as bf16 (hi + optional lo) and / or fp32
 __global__ void k_maxpool2_bf16(const uint4* __restrict__ in, const uint4* __restrict__ in_lo, uint4* __restrict__ out16,
-                                uint4* __restrict__ out16_lo, float* __restrict__ out32, int B, int H, int W, int C8) {
+                                uint4* __restrict__ out16_lo, float* __restrict__ out32, int B, int H, int W, int C8, int f16) {
   const int Ho = H / 2, Wo = W / 2;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)B * Ho * Wo * C8;
@@ -158,7 +163,12 @@ __global__ void k_maxpool2_bf16(const uint4* __restrict__ in, const uint4* __res
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
     float f[8] = {__low2float(h[0]), __high2float(h[0]), __low2float(h[1]), __high2float(h[1]),
                   __low2float(h[2]), __high2float(h[2]), __low2float(h[3]), __high2float(h[3])};
-    if (in_lo) {
+    if (f16) {                                 // input (and 16-bit output) are single IEEE fp16 values
+      const __half2* g = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 t2 = __half22float2(g[k]); f[2 * k] = t2.x; f[2 * k + 1] = t2.y; }
+    }
+    if (in_lo && !f16) {
       const uint4 ql = __ldg(in_lo + base + offs[t]);
       const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&ql);
 #pragma unroll
@@ -167,7 +177,9 @@ __global__ void k_maxpool2_bf16(const uint4* __restrict__ in, const uint4* __res
 #pragma unroll
     for (int k = 0; k < 8; ++k) m[k] = t == 0 ? f[k] : fmaxf(m[k], f[k]);
   }
-  if (out16) {
+  if (out16 && f16) {                          // (the maximum of fp16 values is an fp16 value: exact)
+    out16[i] = make_uint4(pack_f16x2(m[0], m[1]), pack_f16x2(m[2], m[3]), pack_f16x2(m[4], m[5]), pack_f16x2(m[6], m[7]));
+  } else if (out16) {
     uint4 o, l;
     split_bf16x2(m[0], m[1], o.x, l.x); split_bf16x2(m[2], m[3], o.y, l.y);
     split_bf16x2(m[4], m[5], o.z, l.z); split_bf16x2(m[6], m[7], o.w, l.w);
@@ -181,10 +193,10 @@ __global__ void k_maxpool2_bf16(const uint4* __restrict__ in, const uint4* __res
   }
 }
 int maxpool2_nhwc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* in_lo, __nv_bfloat16* out16, __nv_bfloat16* out16_lo, float* out32, int B,
-                       int H, int W, int C, cudaStream_t st) {
+                       int H, int W, int C, cudaStream_t st, int f16) {
   DVD_REQUIRE(in && (out16 || out32) && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bf16: bad args");
   size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-  k_maxpool2_bf16<<<cdiv(total, 256), 256, 0, st>>>((const uint4*)in, (const uint4*)in_lo, (uint4*)out16, (uint4*)out16_lo, out32, B, H, W, C / 8);
+  k_maxpool2_bf16<<<cdiv(total, 256), 256, 0, st>>>((const uint4*)in, (const uint4*)in_lo, (uint4*)out16, (uint4*)out16_lo, out32, B, H, W, C / 8, f16);
   DVD_LAUNCH_CHECK("k_maxpool2_bf16");
   return 0;
 }

@@ -18,9 +18,10 @@ int pack_y4(const float* y512, const float* mask, float* out, int B, cudaStream_
 // 2x2 max pool on NHWC fp32
 int maxpool2_nhwc(const float* in, float* out, int B, int H, int W, int C, cudaStream_t st);
 // 3x3 / pad 1 im2col of a 4-channel NHWC fp32 image into bf16 rows of 64 (k = tap*4 + c, k >= 36 zero): [B*H*W, 64]
-int im2col3x3_c4_bf16(const float* in, __nv_bfloat16* out, __nv_bfloat16* out_lo, int B, int H, int W, cudaStream_t st);
+// (out_f16 != 0: ONE IEEE fp16 value per element in `out` instead of bf16 / a bf16 pair)
+int im2col3x3_c4_bf16(const float* in, __nv_bfloat16* out, __nv_bfloat16* out_lo, int B, int H, int W, cudaStream_t st, int out_f16 = 0);
 int maxpool2_nhwc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* in_lo, __nv_bfloat16* out16, __nv_bfloat16* out16_lo, float* out32, int B,
-                       int H, int W, int C, cudaStream_t st);
+                       int H, int W, int C, cudaStream_t st, int f16 = 0);      // f16: input and 16-bit output are single fp16 values
 // fp32 NHWC -> NCHW (feat for the drop-in model() return value) and back
 int nhwc_to_nchw(const float* in, float* out, int B, int H, int W, int C, cudaStream_t st);
 

@@ -124,6 +124,12 @@ class PackedWeights:
                 h, l = split_bf16(pad)
                 self.keep += [h, l]
                 T.pyr[0].bf16, T.pyr[0].bf16_lo = h.data_ptr(), l.data_ptr()
+            if self.with_bf16:                                              # the same matrices as fp16 pairs (two-pass pyramid of bf16x3)
+                w2 = pad if i == 0 else self.keep[-3]                       # level 0: the K-padded copy; else the fp32 copy _mat made
+                h16, l16 = split_f16(w2)
+                self.keep += [h16, l16]
+                T.pyr_h[i].f32, T.pyr_h[i].bf16, T.pyr_h[i].bf16_lo = T.pyr[i].f32, h16.data_ptr(), l16.data_ptr()
+                T.pyr_h[i].n, T.pyr_h[i].k = int(w2.shape[0]), int(w2.shape[1])
             T.pyr_b[i] = self._vec(sd[p + ".bias"])
         for i, e in enumerate(EMB_KEYS):
             w = sd[f"{e}_embedder.proj.weight"].float()

@@ -103,6 +103,10 @@ typedef struct dvd_weights {
   const float *dec_ln_w, *dec_ln_b;     /* decoder.layer_norm (eps 1e-5)                   */
   dvd_mat_t fin;             const float* fin_b;                       /* [8,1536]         */
   dvd_mat_t fin_ada;         const float* fin_ada_b;                   /* [3072,1536]      */
+  /* DVD_PREC_BF16X3, optional: the pyramid weights (same packing as pyr[], level 0 K-padded to 64) as IEEE fp16 hi / lo pairs in the
+   * bf16 / bf16_lo slots.  When present the pyramid runs two tensor passes (ONE fp16 activation x weight pair; the oracle study finds no
+   * measurable map error from fp16 pyramid activations); NULL pointers: three passes on bf16 pairs. */
+  dvd_mat_t pyr_h[7];
 } dvd_weights_t;
 
 /* Per-step conditioning table row (floats): temb[384] ‖ block adaLN[2304] ‖ final adaLN[3072]. */

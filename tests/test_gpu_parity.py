@@ -279,6 +279,39 @@ def test_gemm_fp16_activation_x_weight_pair(dev, M, N, K):
     assert float((Cg - full).abs().max()) / max(1.0, float(full.abs().max())) < 1e-3
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(2048, 2048, 1536), (512, 192, 128), (256, 64, 64)])
+def test_gemm_decoder_epilogues(dev, mode, M, N, K):
+    """The decoder's epilogue specialisations of the CTA-pair kernel through dvd_gemm_tune: folded BN + ReLU into a bf16 hi/lo pair
+    (conv1: 16-byte stores after the quad transpose) and folded BN + ReLU + in-place fp32 residual (conv2), every tile width."""
+    from dvd_b200 import _lib
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=dev, generator=g) * 0.5
+    W = torch.randn(N, K, device=dev, generator=g) / K ** 0.5
+    sc, sh = torch.rand(N, device=dev, generator=g) + 0.5, torch.randn(N, device=dev, generator=g)
+    Ah, Wh = A.bfloat16(), W.bfloat16()
+    x3 = mode == "bf16x3"
+    Al = (A - Ah.float()).bfloat16() if x3 else None
+    Wl = (W - Wh.float()).bfloat16() if x3 else None
+    a64 = (Ah.double() + Al.double()) if x3 else Ah.double()
+    w64 = (Wh.double() + Wl.double()) if x3 else Wh.double()
+    ref = torch.relu((a64 @ w64.t()) * sc.double() + sh.double())
+    lib = _lib.lib()
+    hi = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    lo = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(lib.dvd_gemm_tune(_lib.ptr(Ah), _lib.ptr(Al), K, _lib.ptr(Wh), _lib.ptr(Wl), K, None, _lib.ptr(sc), _lib.ptr(sh), 1,
+                                 _lib.ptr(hi), _lib.ptr(lo) if x3 else None, None, None, M, N, K, _lib.stream_ptr()), "gemm_tune conv1")
+    got = hi.double() + (lo.double() if x3 else 0.0)
+    tol = 2e-5 if x3 else 1e-2
+    assert float((got - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
+    res = torch.randn(M, N, device=dev, generator=g)
+    want = ref + res.double()
+    _lib.check(lib.dvd_gemm_tune(_lib.ptr(Ah), _lib.ptr(Al), K, _lib.ptr(Wh), _lib.ptr(Wl), K, None, _lib.ptr(sc), _lib.ptr(sh), 1,
+                                 None, None, _lib.ptr(res), _lib.ptr(res), M, N, K, _lib.stream_ptr()), "gemm_tune conv2")
+    torch.cuda.synchronize()
+    assert float((res.double() - want).abs().max()) < 2e-5 * max(1.0, float(want.abs().max()))
+
+
 def test_gemm_bf16_more_row_tiles_than_grid_y(dev):
     """M / 128 > 65535 row tiles (the 512x512 pyramid levels of >= 32 documents in flight): the tile index is folded into
     gridDim.z, with a ragged last z-slice."""
