@@ -317,11 +317,14 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
   const dvd_weights_t& w = *c.w; const Workspace& s = c.ws; cudaStream_t st = c.st;
   const int N = c.docs * c.n_hyp, M = N * 1024;
   const bool tc = c.tc();
-  // DVD_LN_FUSION=1 (opt-in): LayerNorm folded into the decoder GEMMs.  Measured on B200 (profiles/r2_ln_fusion.txt): 370 fewer
-  // launches per 10 documents but 171 vs 178 docs/s at batch 1 (the longer epilogues sit on the exposed tail of each GEMM), equal
-  // at 16 documents in flight, so the separate LayerNorm kernels stay the default.
-  const int want_lnf = getenv("DVD_LN_FUSION") ? atoi(getenv("DVD_LN_FUSION")) : 0;
-  const bool lnf = c.x3() && want_lnf && w.dec[0].qkv_ln.bf16 && w.dec[0].qkv_ln.bf16_lo;
+  // LayerNorm folded into the decoder GEMMs (producers emit row statistics + the raw rows as an operand pair, the consumer normalises
+  // in its epilogue).  DVD_LN_FUSION = 2 (default): norm2 -> conv1 only; 1: norm1 -> q|k|v as well (q|k|v then needs three passes on the
+  // raw rows and loses more than the LayerNorm kernel cost); 0: separate LayerNorm kernels.  Measured on one B200, batch 1
+  // (profiles/r2_ln_fusion.txt): 216.0 (0) / 220.7 (2) / 204.6 (1) docs/s.  Before the GEMM epilogue's cold-code fix the fused variants
+  // lost: every instruction added to an epilogue that ran cold cost several times its warm price.
+  const int want_lnf = getenv("DVD_LN_FUSION") ? atoi(getenv("DVD_LN_FUSION")) : 2;
+  const bool lnf_c1 = c.x3() && want_lnf && w.dec[0].conv1_ln.bf16 && w.dec[0].conv1_ln.bf16_lo && w.dec[0].conv1_colsum;   // norm2 -> conv1
+  const bool lnf = lnf_c1 && want_lnf == 1 && w.dec[0].qkv_ln.bf16 && w.dec[0].qkv_ln.bf16_lo && w.dec[0].qkv_colsum;         // + norm1 -> q|k|v
   // The decoder's q|k|v GEMM (the largest of the step) takes its activation as ONE fp16 value: q, k and v are rounded to fp16 for the
   // attention anyway, and what moves the map is weight rounding, not activation rounding (oracle/precision_study.py
   // --decoder-breakdown: 1.44e-6 -> 1.52e-6 mean map error).  Two tensor passes instead of three.  DVD_QKV_3PASS=1 restores the pair.
@@ -403,7 +406,7 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     // h- and w-branch side by side: conv1x1 + ReLU, then conv1x1 + sigmoid (CA:143-157)
     DVD_TRY(gemv_pair(mean, mean, 1536, w.h_scale0.f32, w.w_scale0.f32, w.h_scale0_b, w.w_scale0_b, hs1, ws1, 1536, N, 1536, 1536, 1, st));
     DVD_TRY(gemv_pair(hs1, ws1, 1536, w.h_scale2.f32, w.w_scale2.f32, w.h_scale2_b, w.w_scale2_b, hs, wsv, 1536, N, 1536, 1536, 3, st));
-    // DVD_LN_FUSION=1: the decoder's twelve LayerNorms are folded into the GEMMs that consume them (no LN kernel, no normalised copy):
+    // DVD_LN_FUSION=1: all twelve LayerNorms of the decoder are folded into the GEMMs that consume them (no LN kernel, no normalised copy):
     // every producer of the residual stream X also writes X as an operand pair and the rows' partial (sum, sum of squares); the QKV /
     // conv1 GEMMs multiply the RAW rows by gamma-scaled weights and normalise in the epilogue (Epilogue::ln_*).  Accuracy checked on
     // the oracle first (oracle/precision_study.py --ln-fusion: 1.44e-6 -> 1.53e-6 mean map error).
@@ -430,14 +433,14 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
                       s.att_d, s.att_d16, 1536, N, 256, 0.0625f, 1));
     {
       Epilogue e; e.resid = s.X; e.ldr = 1536; e.out = s.X; e.ldc = 1536;
-      if (lnf) { out_operand(e, s.X16, 1536); e.stats_out = s.lnstats; }
+      if (lnf_c1) { out_operand(e, s.X16, 1536); e.stats_out = s.lnstats; }
       DVD_TRY(linear(c, s.att_d, s.att_d16, 1536, L.fc, 0, M, 1536, e));
     }
-    if (!lnf) DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n2_w, L.n2_b, nullptr, nullptr, st));
+    if (!lnf_c1) DVD_TRY(layernorm(s.X, 1536, tc ? nullptr : s.hd, 1536, s.hd16.hi, s.hd16.lo, 1536, M, 1536, 1e-5f, L.n2_w, L.n2_b, nullptr, nullptr, st));
     {
       Epilogue e; e.scale = L.bn1_scale; e.shift = L.bn1_shift; e.act = ACT_RELU; e.out = tc ? nullptr : s.f1; e.ldc = 2048;
       if (tc) out_operand(e, s.f116, 2048);
-      if (lnf) {
+      if (lnf_c1) {
         e.ln_stats = s.lnstats; e.ln_colsum = L.conv1_colsum; e.ln_chunks = 48; e.ln_eps = 1e-5f; e.bias = L.conv1_cvec;
         DVD_TRY(linear(c, nullptr, s.X16, 1536, L.conv1_ln, 0, M, 2048, e));
       } else {
