@@ -317,18 +317,19 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
   const dvd_weights_t& w = *c.w; const Workspace& s = c.ws; cudaStream_t st = c.st;
   const int N = c.docs * c.n_hyp, M = N * 1024;
   const bool tc = c.tc();
-  // LayerNorm folded into the decoder GEMMs (producers emit row statistics + the raw rows as an operand pair, the consumer normalises
-  // in its epilogue).  DVD_LN_FUSION = 2 (default): norm2 -> conv1 only; 1: norm1 -> q|k|v as well (q|k|v then needs three passes on the
-  // raw rows and loses more than the LayerNorm kernel cost); 0: separate LayerNorm kernels.  Measured on one B200, batch 1
-  // (profiles/r2_ln_fusion.txt): 216.0 (0) / 220.7 (2) / 204.6 (1) docs/s.  Before the GEMM epilogue's cold-code fix the fused variants
-  // lost: every instruction added to an epilogue that ran cold cost several times its warm price.
-  const int want_lnf = getenv("DVD_LN_FUSION") ? atoi(getenv("DVD_LN_FUSION")) : 2;
+  // LayerNorm folded into the decoder GEMMs (producers emit row statistics + the raw rows as a 16-bit operand, the consumer normalises
+  // in its epilogue).  DVD_LN_FUSION = 1 (default): norm2 -> conv1 (raw rows as a bf16 pair, three passes) AND norm1 -> q|k|v (raw rows
+  // as ONE fp16 value, two passes; oracle: 1.2e-6 -> 1.8e-6 mean map error): no LayerNorm kernel left in the decoder; 2: norm2 -> conv1
+  // only; 0: separate LayerNorm kernels.  Measured in profiles/r2_ln_fusion.txt.  Before the GEMM epilogue's cold-code fix the fused variants lost: every instruction added to an
+  // epilogue that ran cold cost several times its warm price.
+  const int want_lnf = getenv("DVD_LN_FUSION") ? atoi(getenv("DVD_LN_FUSION")) : 1;
   const bool lnf_c1 = c.x3() && want_lnf && w.dec[0].conv1_ln.bf16 && w.dec[0].conv1_ln.bf16_lo && w.dec[0].conv1_colsum;   // norm2 -> conv1
   const bool lnf = lnf_c1 && want_lnf == 1 && w.dec[0].qkv_ln.bf16 && w.dec[0].qkv_ln.bf16_lo && w.dec[0].qkv_colsum;         // + norm1 -> q|k|v
   // The decoder's q|k|v GEMM (the largest of the step) takes its activation as ONE fp16 value: q, k and v are rounded to fp16 for the
   // attention anyway, and what moves the map is weight rounding, not activation rounding (oracle/precision_study.py
   // --decoder-breakdown: 1.44e-6 -> 1.52e-6 mean map error).  Two tensor passes instead of three.  DVD_QKV_3PASS=1 restores the pair.
   const bool qkv_a16 = c.x3() && !lnf && w.dec[0].qkv_h.bf16 && w.dec[0].qkv_h.bf16_lo && !(getenv("DVD_QKV_3PASS") && atoi(getenv("DVD_QKV_3PASS")));
+  // (with norm1 folded the q|k|v GEMM is always two-pass: qkv_ln is packed as an fp16 pair and the raw rows arrive as ONE fp16 value)
   const float* ada = trow + 384;                 // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
   const float* fin = trow + 384 + 2304;          // shift[1536], scale[1536]
   auto off16 = [](const B16& b, size_t n) { B16 r; r.hi = b.hi + n; r.lo = b.lo ? b.lo + n : nullptr; return r; };
@@ -410,7 +411,7 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     // every producer of the residual stream X also writes X as an operand pair and the rows' partial (sum, sum of squares); the QKV /
     // conv1 GEMMs multiply the RAW rows by gamma-scaled weights and normalise in the epilogue (Epilogue::ln_*).  Accuracy checked on
     // the oracle first (oracle/precision_study.py --ln-fusion: 1.44e-6 -> 1.53e-6 mean map error).
-    if (lnf) DVD_TRY(posenc_add_ln(s.X, hs, wsv, w.dec_hpe, w.dec_wpe, N, 1536, s.X16.hi, s.X16.lo, s.lnstats, 48, st));
+    if (lnf) DVD_TRY(posenc_add_ln(s.X, hs, wsv, w.dec_hpe, w.dec_wpe, N, 1536, s.X16.hi, nullptr, s.lnstats, 48, st, 1));
     else DVD_TRY(posenc_add(s.X, hs, wsv, w.dec_hpe, w.dec_wpe, N, 1536, st));
   }
   if (g_stop_after == 2) return 0;
@@ -424,7 +425,7 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
       if (tc) { out_attn(c, e, s.qkv_d16, 4608); e.vt_out = s.vt_d16; e.vt_col0 = 3072; }
       if (lnf) {
         e.ln_stats = s.lnstats; e.ln_colsum = L.qkv_colsum; e.ln_chunks = 48; e.ln_eps = 1e-5f; e.bias = L.qkv_cvec;
-        DVD_TRY(linear(c, nullptr, s.X16, 1536, L.qkv_ln, 0, M, 4608, e));
+        DVD_TRY(linear(c, nullptr, s.X16, 1536, L.qkv_ln, 0, M, 4608, e, true));
       } else {
         DVD_TRY(linear(c, s.hd, s.hd16, 1536, qkv_a16 ? L.qkv_h : L.qkv, 0, M, 4608, e, qkv_a16));
       }
@@ -451,7 +452,7 @@ static int denoise_step(const Ctx& c, const float* x_t, const float* init_flow, 
     else DVD_TRY(dwconv3x3_bn_relu(s.f1, L.dw_w, L.bn2_scale, L.bn2_shift, s.f2, nullptr, N, 2048, st));
     {
       Epilogue e; e.scale = L.bn3_scale; e.shift = L.bn3_shift; e.act = ACT_RELU; e.resid = s.X; e.ldr = 1536; e.out = s.X; e.ldc = 1536;
-      if (lnf) { out_operand(e, s.X16, 1536); e.stats_out = s.lnstats; }
+      if (lnf) { e.out_bf16 = s.X16.hi; e.out_lo = nullptr; e.ldc_bf16 = 1536; e.out_f16 = 1; e.stats_out = s.lnstats; }     // raw rows as ONE fp16
       DVD_TRY(linear(c, s.f2, s.f216, 2048, L.conv2, 0, M, 1536, e));
     }
     if (g_stop_after == 3 + l) return 0;

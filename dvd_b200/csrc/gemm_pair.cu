@@ -190,7 +190,7 @@ __device__ __forceinline__ void epi_rows(const Epilogue& e, const Frag& f, const
       if ((O == EO_F32 || O == EO_F32X) && live) *reinterpret_cast<float2*>(e.out + o32 + 8 * j) = make_float2(v0, v1);
       if (O == EO_F32X) { s1 += v0 + v1; s2 += v0 * v0 + v1 * v1; }
       if (O == EO_PAIR || (O == EO_F32X && e.out_lo)) split_bf16x2(v0, v1, hi[j], lo[j]);
-      else if (O == EO_F16) hi[j] = pack_f16x2(v0, v1);
+      else if (O == EO_F16 || (O == EO_F32X && e.out_f16)) hi[j] = pack_f16x2(v0, v1);
       else if (OUT16) hi[j] = pack_bf16x2(v0, v1);
     }
     if (OUT16) {
@@ -266,7 +266,7 @@ static int classify_epilogue(const Epilogue& e) {
   if (e.resid) f |= EF_RES;
   if (e.ln_stats) f |= EF_LN;
   int o;
-  if (e.out && e.out_bf16 && e.stats_out && !e.out_f16) o = EO_F32X;
+  if (e.out && e.out_bf16 && e.stats_out && !(e.out_f16 && e.out_lo)) o = EO_F32X;      // 16-bit copy: bf16, bf16 pair or ONE fp16
   else if (e.stats_out) return EPI_GENERIC;                   // (rejected by the dispatcher: statistics need the compiled body)
   else if (e.out && !e.out_bf16) o = EO_F32;
   else if (!e.out && e.out_bf16) o = e.out_lo ? EO_PAIR : (e.out_f16 ? EO_F16 : EO_BF16);

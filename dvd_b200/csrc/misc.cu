@@ -554,7 +554,7 @@ int posenc_add(float* X, const float* hs, const float* ws, const float* hpe, con
 // pair) and its (sum, sum of squares) for the LayerNorm that GEMM's epilogue applies (slot 0 = whole row, the other chunk slots zero).
 __global__ void __launch_bounds__(256) k_posenc_ln(float* __restrict__ X, const float4* __restrict__ hs, const float4* __restrict__ ws,
                                                    const float4* __restrict__ hpe, const float4* __restrict__ wpe, __nv_bfloat16* __restrict__ hi,
-                                                   __nv_bfloat16* __restrict__ lo, float* __restrict__ stats, int chunks, int rows) {
+                                                   __nv_bfloat16* __restrict__ lo, float* __restrict__ stats, int chunks, int rows, int f16) {
   constexpr int C4 = 384;                       // 1536 / 4
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -572,10 +572,14 @@ __global__ void __launch_bounds__(256) k_posenc_ln(float* __restrict__ X, const 
     x.z = (x.z + a.z * hp.z) + b.z * wp.z; x.w = (x.w + a.w * hp.w) + b.w * wp.w;
     xr[c] = x;
     uint2 u, l;
-    split_bf16x2(x.x, x.y, u.x, l.x);
-    split_bf16x2(x.z, x.w, u.y, l.y);
+    if (f16) {                                  // ONE fp16 value per element (operand of the two-pass q|k|v GEMM)
+      u.x = pack_f16x2(x.x, x.y); u.y = pack_f16x2(x.z, x.w);
+    } else {
+      split_bf16x2(x.x, x.y, u.x, l.x);
+      split_bf16x2(x.z, x.w, u.y, l.y);
+    }
     *reinterpret_cast<uint2*>(hi + ((size_t)row * C4 + c) * 4) = u;
-    if (lo) *reinterpret_cast<uint2*>(lo + ((size_t)row * C4 + c) * 4) = l;
+    if (lo && !f16) *reinterpret_cast<uint2*>(lo + ((size_t)row * C4 + c) * 4) = l;
     s1 += (x.x + x.y) + (x.z + x.w);
     s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
   }
@@ -584,11 +588,11 @@ __global__ void __launch_bounds__(256) k_posenc_ln(float* __restrict__ X, const 
   for (int k = lane; k < chunks; k += 32) sr[k] = k == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
 }
 int posenc_add_ln(float* X, const float* hs, const float* ws, const float* hpe, const float* wpe, int N, int C, __nv_bfloat16* x16,
-                  __nv_bfloat16* x16_lo, float* stats, int chunks, cudaStream_t st) {
+                  __nv_bfloat16* x16_lo, float* stats, int chunks, cudaStream_t st, int x16_f16) {
   DVD_REQUIRE(X && hs && ws && hpe && wpe && x16 && stats && C == 1536 && chunks == C / 32, "posenc_add_ln: bad args");
   const int rows = N * 1024;
   k_posenc_ln<<<cdiv(rows, 8), 256, 0, st>>>(X, (const float4*)hs, (const float4*)ws, (const float4*)hpe, (const float4*)wpe, x16, x16_lo, stats,
-                                             chunks, rows);
+                                             chunks, rows, x16_f16);
   DVD_LAUNCH_CHECK("k_posenc_ln");
   return 0;
 }

@@ -65,7 +65,7 @@ int posenc_add(float* X, const float* hs, const float* ws, const float* hpe, con
 // same + the row as 16-bit GEMM operand (x16 [+ x16_lo]) + per-row (sum, sum of squares) in `stats` [N*1024][chunks][2] (slot 0), for the
 // LayerNorm fused into the next GEMM's epilogue (Epilogue::ln_stats).  C = 1536, chunks = C / 32.
 int posenc_add_ln(float* X, const float* hs, const float* ws, const float* hpe, const float* wpe, int N, int C, __nv_bfloat16* x16,
-                  __nv_bfloat16* x16_lo, float* stats, int chunks, cudaStream_t st);
+                  __nv_bfloat16* x16_lo, float* stats, int chunks, cudaStream_t st, int x16_f16 = 0);
 
 // depthwise 3x3 (pad 1) over the 32x32 token grid + folded BN + ReLU, token-major [N,1024,C]  (CA:33-41)
 int dwconv3x3_bn_relu(const float* in, const float* w9c, const float* scale, const float* shift, float* out,

@@ -98,10 +98,15 @@ class PackedWeights:
             m.bf16, m.bf16_lo = h.data_ptr(), l.data_ptr()
         return m
 
-    def _ln_fold(self, w64: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    def _ln_fold(self, w64: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, f16: bool = False):
+        """W' = W * gamma as a 16-bit pair (bf16, or IEEE fp16 for the two-pass q|k|v GEMM), the column sums of the ROUNDED pair, W beta."""
         wp = (w64 * gamma.double()[None, :]).float()
-        m = self._mat(wp)
-        hi, lo = self.keep[-2], self.keep[-1]                      # the pair _mat just made
+        m = self._mat(wp, bf16=not f16)
+        if f16:
+            h16, l16 = split_f16(self.keep[-1])                    # (the fp32 copy _mat just made)
+            self.keep += [h16, l16]
+            m.bf16, m.bf16_lo = h16.data_ptr(), l16.data_ptr()
+        hi, lo = self.keep[-2], self.keep[-1]                      # the pair that is used
         colsum = (hi.double() + lo.double()).sum(1).float()
         cvec = (w64 @ beta.double()).float()
         return m, self._vec(colsum), self._vec(cvec)
@@ -177,7 +182,7 @@ class PackedWeights:
                 # LayerNorm folded into the consumer GEMMs (fused-LN epilogue, csrc/gemm_pair.cu): W' = W * gamma, colsum of the ROUNDED
                 # pair, cvec = W beta (float64 sums)
                 wq = torch.cat([sd[p + "attn.linear_q.weight"], sd[p + "attn.linear_k.weight"], sd[p + "attn.linear_v.weight"]], 0).double()
-                L.qkv_ln, L.qkv_colsum, L.qkv_cvec = self._ln_fold(wq, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+                L.qkv_ln, L.qkv_colsum, L.qkv_cvec = self._ln_fold(wq, sd[p + "norm1.weight"], sd[p + "norm1.bias"], f16=True)
                 wc = sd[f + "conv1.conv.weight"].reshape(2048, 1536).double()
                 L.conv1_ln, L.conv1_colsum, L.conv1_cvec = self._ln_fold(wc, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
         T.dec_ln_w, T.dec_ln_b = self._vec(sd["decoder.layer_norm.weight"]), self._vec(sd["decoder.layer_norm.bias"])

@@ -74,7 +74,7 @@ typedef struct dvd_dec_layer {          /* CA:343-396 DecoderLayer, CA:13-57 fee
    * rounded to fp16 for the attention anyway).  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, so these weights are ALSO
    * packed as an IEEE fp16 pair: qkv_h.bf16 = fp16(W), qkv_h.bf16_lo = fp16(W - fp16(W)).  NULL pointers: the three-pass path runs. */
   dvd_mat_t qkv_h;                      /* [4608,1536], fp16 hi / lo in the bf16 / bf16_lo slots */
-  dvd_mat_t qkv_ln;                     /* [4608,1536] = qkv * norm1.weight               */
+  dvd_mat_t qkv_ln;                     /* [4608,1536] = qkv * norm1.weight, as an IEEE fp16 hi / lo pair (two-pass GEMM on fp16 raw rows) */
   const float *qkv_colsum, *qkv_cvec;   /* [4608]                                         */
   dvd_mat_t conv1_ln;                   /* [2048,1536] = conv1 * norm2.weight             */
   const float *conv1_colsum, *conv1_cvec;   /* [2048]                                     */
