@@ -403,12 +403,16 @@ def test_static_forward_and_first_step_fp32(dev, models, state_dict_live, golden
 STAGE_TOL = {"fp32": 1e-4, "bf16x3": 2e-4, "bf16": 6e-2}      # max abs error against the reference's stage outputs (values are O(1..10))
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16", "bf16x3+lnfusion2", "bf16x3+lnfusion0"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16", "bf16x3+lnfusion2", "bf16x3+lnfusion0", "bf16x3+3pass"])
 def test_block11_and_decoder_stages_match_reference(dev, models, state_dict_live, golden_dir, prec, monkeypatch):
     """Stage-level outputs of the first denoiser forward against hooks on the UNMODIFIED reference (oracle/make_golden.py):
     DiT block 11 (x4,x3,x2,x1), adaptive positional encoding, decoder layer 0 and the decoder output (after decoder.layer_norm)."""
     import torch.nn.functional as F
     from dvd_b200 import _lib
+    if prec.endswith("+3pass"):                                    # three tensor passes everywhere, separate LayerNorm kernels (the round's first bf16x3)
+        for k, v in (("DVD_LN_FUSION", "0"), ("DVD_QKV_3PASS", "1"), ("DVD_PYR_3PASS", "1")):
+            monkeypatch.setenv(k, v)
+        prec = "bf16x3"
     if "+lnfusion" in prec:                                        # variants of the LayerNorm folding (denoiser.cu); default 1 = norm1 and norm2 folded
         monkeypatch.setenv("DVD_LN_FUSION", prec[-1])              # 2: norm2 -> conv1 only, 0: separate LayerNorm kernels
         prec = "bf16x3"
