@@ -438,7 +438,7 @@ def run_ours(a):
         peaks, which = measured_peaks()
         prof = pipe.profile_kernels(dev_sets[0])                             # CUDA-event timing of the dominant kernels, L2-flushed
         gflop = algorithmic_gflop_per_doc(a.diffusion_steps, a.n_batch) * a.docs
-        dtype = {"bf16x3": "bf16x3 (split 16-bit operand pairs, 3 tcgen05 passes per k-step - 2 in the decoder q|k|v GEMM -, fp32 accumulate: fp32-accurate)", "bf16": "bf16", "fp32": "f32"}[a.precision]
+        dtype = {"bf16x3": "bf16x3 (split 16-bit operand pairs, 3 tcgen05 passes per k-step - 2 in the decoder q|k|v GEMMs and the pyramid convs -, fp32 accumulate: fp32-accurate)", "bf16": "bf16", "fp32": "f32"}[a.precision]
         line = {"metric": "dewarped docs/sec (sampling+unwarp)", "value": value, "unit": "docs/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": tot_dev / a.steps * 1e3, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config_dict(a),
