@@ -65,6 +65,7 @@ struct PairCfg {
 struct PairParams {
   int M, N, K;
   int tiles_n, units, npairs;
+  int late_tile0;                 // column tiles >= late_tile0 are scheduled FIRST (0: natural order)
   int conv_h, conv_w, conv_cin;
   int epi;                        // epi_key(flags, out) of a compiled epilogue body, or EPI_GENERIC
 };
@@ -301,7 +302,16 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)
 struct PairUnit { int m0, n0, kb0, kb1; };
 __device__ __forceinline__ PairUnit decode_unit(const PairParams& p, int u, int nkb, int bn) {
   PairUnit q;
-  const int mt = u / p.tiles_n, nt = u - mt * p.tiles_n;
+  int mt, nt;
+  if (p.late_tile0 > 0) {
+    // q|k|v with a transposed V store: the V tiles' epilogue (2-byte scattered stores on top of the normal ones) is the slow one, so all
+    // V tiles are dealt first - they land in the first wave, where the epilogue overlaps the pair's next main loop
+    const int nv = p.tiles_n - p.late_tile0, first = nv * (p.M / (2 * PBM));
+    if (u < first) { mt = u / nv; nt = p.late_tile0 + (u - mt * nv); }
+    else { const int v = u - first; mt = v / p.late_tile0; nt = v - mt * p.late_tile0; }
+  } else {
+    mt = u / p.tiles_n; nt = u - mt * p.tiles_n;
+  }
   q.m0 = mt * (2 * PBM); q.n0 = nt * bn;
   q.kb0 = 0; q.kb1 = nkb;
   return q;
@@ -674,6 +684,7 @@ static int launch_pair(const TcMat& A, const TcMat& W, int M, int N, int K, cons
   p.npairs = units < npairs_max ? (int)units : npairs_max;
   p.conv_h = conv_h; p.conv_w = conv_w; p.conv_cin = conv_cin;
   p.epi = classify_epilogue(e);
+  p.late_tile0 = (e.vt_out && e.vt_col0 > 0 && e.vt_col0 % BN == 0 && e.vt_col0 < N) ? e.vt_col0 / BN : 0;
   if (g_debug) fprintf(stderr, "[gemm_pair] M=%d N=%d K=%d mode=%d conv=%d bn=%d units=%d npairs=%d (max %d) stages=%d smem=%d\n", M, N, K,
                        MODE, (int)CONV, BN, p.units, p.npairs, npairs_max, Cfg::STAGES, Cfg::SMEM);
   DVD_CUDA(launch_pdl_cluster(1, kern, dim3(2 * p.npairs), dim3(PP_THREADS), (size_t)Cfg::SMEM, st, 2, 1, tmA, tmAl, tmB, tmBl, p, e));
