@@ -278,6 +278,8 @@ int patchify_nhwc(const float* in, float* A, __nv_bfloat16* A16, __nv_bfloat16* 
 __global__ void __launch_bounds__(256) k_build_r(const float* __restrict__ flow, const float* __restrict__ feat,
                                                  const float* __restrict__ init_feat, int init_feat_div, int mode,
                                                  float* __restrict__ A, Out16 A16, int lda, int n_hyp) {
+  pdl_trigger();                                    // programmatic dependent launch: the successor may be scheduled now,
+  pdl_wait();                                       // and this kernel was possibly scheduled before its predecessor finished
   const int row = blockIdx.x;                  // (n*32 + h)*32 + w
   const int w = row % 32, h = (row / 32) % 32, n = row / 1024;
   const int c = threadIdx.x;                   // feature channel 0..255
@@ -324,13 +326,15 @@ __global__ void __launch_bounds__(256) k_build_r(const float* __restrict__ flow,
 int build_r_operand(const float* init_flow, const float* feat_nhwc, const float* init_feat_nchw, int init_feat_div, int mode,
                     float* A, __nv_bfloat16* A16, __nv_bfloat16* A16_lo, int lda, int N, int n_hyp, cudaStream_t st) {
   DVD_REQUIRE(init_flow && feat_nhwc && (A || A16) && lda >= 1032 && lda % 4 == 0 && n_hyp > 0 && init_feat_div > 0, "build_r: bad args");
-  k_build_r<<<N * 1024, 256, 0, st>>>(init_flow, feat_nhwc, init_feat_nchw, init_feat_div, mode, A, Out16{A16, A16_lo}, lda, n_hyp);
+  DVD_CUDA(launch_pdl(16, k_build_r, dim3(N * 1024), dim3(256), (size_t)0, st, init_flow, feat_nhwc, init_feat_nchw, init_feat_div, mode, A, Out16{A16, A16_lo}, lda, n_hyp));
   DVD_LAUNCH_CHECK("k_build_r");
   return 0;
 }
 
 __global__ void k_obs_embed(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                             const float* __restrict__ pos, float* __restrict__ out, size_t total) {
+  pdl_trigger();                                    // programmatic dependent launch: the successor may be scheduled now,
+  pdl_wait();                                       // and this kernel was possibly scheduled before its predecessor finished
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int j = i % kHid; size_t row = i / kHid;
@@ -349,7 +353,7 @@ __global__ void k_obs_embed(const float* __restrict__ x, const float* __restrict
 int obs_embed(const float* x, const float* W, const float* bias, const float* pos, float* out, int N, cudaStream_t st) {
   DVD_REQUIRE(x && W && bias && pos && out, "obs_embed: null");
   size_t total = (size_t)N * 1024 * kHid;
-  k_obs_embed<<<cdiv(total, 256), 256, 0, st>>>(x, W, bias, pos, out, total);
+  DVD_CUDA(launch_pdl(16, k_obs_embed, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, x, W, bias, pos, out, total));
   DVD_LAUNCH_CHECK("k_obs_embed");
   return 0;
 }
@@ -513,6 +517,8 @@ int timestep_embedding(const float* t, float* out, int rows, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------ decoder positional encoding
 // deterministic two-stage mean: 32 token chunks of 32, then a fixed-order finish
 __global__ void __launch_bounds__(128) k_token_partial(const float* __restrict__ X, float* __restrict__ part, int C) {
+  pdl_trigger();                                    // programmatic dependent launch: the successor may be scheduled now,
+  pdl_wait();                                       // and this kernel was possibly scheduled before its predecessor finished
   const int c = blockIdx.x * 128 + threadIdx.x, chunk = blockIdx.y, n = blockIdx.z;
   if (c >= C) return;
   const float* p = X + ((size_t)n * 1024 + chunk * 32) * C + c;
@@ -522,6 +528,8 @@ __global__ void __launch_bounds__(128) k_token_partial(const float* __restrict__
   part[((size_t)n * 32 + chunk) * C + c] = s;
 }
 __global__ void k_token_finish(const float* __restrict__ part, float* __restrict__ out, int C, int total) {
+  pdl_trigger();                                    // programmatic dependent launch: the successor may be scheduled now,
+  pdl_wait();                                       // and this kernel was possibly scheduled before its predecessor finished
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int n = i / C, c = i % C;
@@ -533,15 +541,17 @@ int token_mean(const float* X, float* out, int N, int C, cudaStream_t st) {
   // `out` must have room for N*C results followed by N*32*C partials
   DVD_REQUIRE(X && out, "token_mean: null");
   float* part = out + (size_t)N * C;
-  k_token_partial<<<dim3(cdiv(C, 128), 32, N), 128, 0, st>>>(X, part, C);
+  DVD_CUDA(launch_pdl(16, k_token_partial, dim3(cdiv(C, 128), 32, N), dim3(128), (size_t)0, st, X, part, C));
   DVD_LAUNCH_CHECK("k_token_partial");
-  k_token_finish<<<cdiv(N * C, 256), 256, 0, st>>>(part, out, C, N * C);
+  DVD_CUDA(launch_pdl(16, k_token_finish, dim3(cdiv(N * C, 256)), dim3(256), (size_t)0, st, (const float*)part, out, C, N * C));
   DVD_LAUNCH_CHECK("k_token_finish");
   return 0;
 }
 
 __global__ void k_posenc_add(float4* __restrict__ X, const float4* __restrict__ hs, const float4* __restrict__ ws,
                              const float4* __restrict__ hpe, const float4* __restrict__ wpe, int C4, size_t total) {
+  pdl_trigger();                                    // programmatic dependent launch: the successor may be scheduled now,
+  pdl_wait();                                       // and this kernel was possibly scheduled before its predecessor finished
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = i % C4; size_t row = i / C4;
@@ -556,8 +566,8 @@ __global__ void k_posenc_add(float4* __restrict__ X, const float4* __restrict__ 
 int posenc_add(float* X, const float* hs, const float* ws, const float* hpe, const float* wpe, int N, int C, cudaStream_t st) {
   DVD_REQUIRE(X && hs && ws && hpe && wpe && C % 4 == 0, "posenc_add: bad args");
   size_t total = (size_t)N * 1024 * (C / 4);
-  k_posenc_add<<<cdiv(total, 256), 256, 0, st>>>((float4*)X, (const float4*)hs, (const float4*)ws, (const float4*)hpe,
-                                                 (const float4*)wpe, C / 4, total);
+  DVD_CUDA(launch_pdl(16, k_posenc_add, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, (float4*)X, (const float4*)hs, (const float4*)ws,
+                      (const float4*)hpe, (const float4*)wpe, C / 4, total));
   DVD_LAUNCH_CHECK("k_posenc_add");
   return 0;
 }
@@ -567,6 +577,8 @@ int posenc_add(float* X, const float* hs, const float* ws, const float* hpe, con
 __global__ void __launch_bounds__(256) k_posenc_ln(float* __restrict__ X, const float4* __restrict__ hs, const float4* __restrict__ ws,
                                                    const float4* __restrict__ hpe, const float4* __restrict__ wpe, __nv_bfloat16* __restrict__ hi,
                                                    __nv_bfloat16* __restrict__ lo, float* __restrict__ stats, int chunks, int rows, int f16) {
+  pdl_trigger();                                    // programmatic dependent launch: the successor may be scheduled now,
+  pdl_wait();                                       // and this kernel was possibly scheduled before its predecessor finished
   constexpr int C4 = 384;                       // 1536 / 4
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -603,8 +615,8 @@ int posenc_add_ln(float* X, const float* hs, const float* ws, const float* hpe, 
                   __nv_bfloat16* x16_lo, float* stats, int chunks, cudaStream_t st, int x16_f16) {
   DVD_REQUIRE(X && hs && ws && hpe && wpe && x16 && stats && C == 1536 && chunks == C / 32, "posenc_add_ln: bad args");
   const int rows = N * 1024;
-  k_posenc_ln<<<cdiv(rows, 8), 256, 0, st>>>(X, (const float4*)hs, (const float4*)ws, (const float4*)hpe, (const float4*)wpe, x16, x16_lo, stats,
-                                             chunks, rows, x16_f16);
+  DVD_CUDA(launch_pdl(16, k_posenc_ln, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, st, X, (const float4*)hs, (const float4*)ws, (const float4*)hpe,
+                      (const float4*)wpe, x16, x16_lo, stats, chunks, rows, x16_f16));
   DVD_LAUNCH_CHECK("k_posenc_ln");
   return 0;
 }
@@ -745,6 +757,8 @@ __global__ void __launch_bounds__(256) k_final(const float* __restrict__ X, cons
                                                const float* __restrict__ W8, const float* __restrict__ b8,
                                                const float* __restrict__ init_flow, const float* __restrict__ x_t, float a, float b,
                                                float* __restrict__ pred, float* __restrict__ x_prev, int rows) {
+  pdl_trigger();                                    // programmatic dependent launch: the successor may be scheduled now,
+  pdl_wait();                                       // and this kernel was possibly scheduled before its predecessor finished
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   constexpr int NV = 12, C = 1536;
@@ -814,7 +828,7 @@ int final_layer(const float* X, const float* ln_w, const float* ln_b, const floa
                 const float* b8, const float* init_flow, const float* x_t, float a, float b, float* pred, float* x_prev, int N,
                 cudaStream_t st) {
   DVD_REQUIRE(X && ln_w && ln_b && shift && scale && W8 && b8 && init_flow && pred && (x_t || !x_prev), "final_layer: null");
-  k_final<<<cdiv(N * 1024, 8), 256, 0, st>>>(X, ln_w, ln_b, shift, scale, W8, b8, init_flow, x_t, a, b, pred, x_prev, N * 1024);
+  DVD_CUDA(launch_pdl(16, k_final, dim3(cdiv(N * 1024, 8)), dim3(256), (size_t)0, st, X, ln_w, ln_b, shift, scale, W8, b8, init_flow, x_t, a, b, pred, x_prev, N * 1024));
   DVD_LAUNCH_CHECK("k_final");
   return 0;
 }
